@@ -1,0 +1,20 @@
+"""B200-native feature front-end of gan-police/audiodeepfake-detection (wavelet packets, STFT, Haar fingerprint).
+
+The compute path is hand-written CUDA for sm_100a in ``libafd_b200.so`` (C ABI: include/afd_b200.h); this package
+is the thin host-side mirror of the reference's transform-module API.  No CPU fallback exists by design.
+"""
+from .wavelets import Wavelet, get_wavelet  # noqa: F401
+from .wavelet_math import (  # noqa: F401
+    Packets,
+    STFTLayer,
+    Normalize,
+    compute_pytorch_packet_representation,
+    get_transforms,
+    normalization_stats,
+    stft_power_features,
+    wavelet_packet_features,
+    wpt_out_len,
+    stft_out_shape,
+)
+
+__version__ = "0.1.0"

@@ -1,0 +1,125 @@
+/*
+ * afd_b200.h -- C ABI of the B200-native audio-deepfake feature front-end (libafd_b200.so).
+ *
+ * Drop-in boundary for the feature front-end of gan-police/audiodeepfake-detection ("the reference";
+ * all file:line citations are relative to the reference checkout).  The reference has no FFI layer: its
+ * boundary is a torch.nn.Module contract (src/audiofakedetect/wavelet_math.py:266-384).  Each entry point
+ * below replaces one third-party call the reference makes on that path; the Python modules in
+ * audiodeepfake-detection_b200/wavelet_math.py keep the reference's module API and call these through
+ * ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device entry points are
+ *     asynchronous and stream-ordered; they never synchronise the device.
+ *   - the library is stateless (filter taps travel as kernel parameters), hence thread-safe per stream.
+ *   - return value: AFD_OK (0), a negative AFD_ERR_* validation code, or a positive cudaError_t.
+ *     afd_last_error() returns a thread-local human-readable message for the last non-zero return.
+ *   - all arithmetic is IEEE fp32 (FMA), like the reference's fp32 tensors.
+ */
+#ifndef AFD_B200_H
+#define AFD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFD_OK 0
+#define AFD_ERR_INVALID_ARG (-1)   /* null pointer, non-positive size, odd / unsupported filter length ... */
+#define AFD_ERR_UNSUPPORTED (-2)   /* valid request this build cannot serve (e.g. tree does not fit in shared memory) */
+#define AFD_ERR_REFLECT_PAD (-3)   /* a node is not longer than the reflect padding (torch F.pad would raise too) */
+#define AFD_ERR_NO_DEVICE (-4)
+
+#define AFD_ORDER_FREQ 0           /* Gray-code / frequency order: ptwt get_level(), pywt order="freq" */
+#define AFD_ORDER_NATURAL 1
+
+/* Library version (major*10000 + minor*100 + patch). */
+int afd_version(void);
+
+/* Thread-local message for the most recent failing call on this thread ("" if none). */
+const char* afd_last_error(void);
+
+/*
+ * Number of coefficients per node after `level` analysis steps on a length-N signal with an F-tap filter:
+ * n <- floor((n + F - 1) / 2), `level` times  (ptwt _get_pad / pywt dwt_coeff_len).
+ * Replaces: shape inference the reference does by running the transform once (utils.py:589-621).
+ */
+int afd_wpt_out_len(int64_t N, int F, int level, int64_t* T_out);
+
+/*
+ * Fused wavelet-packet feature transform.
+ * Replaces: ptwt.WaveletPacket(data, wavelet, mode="reflect") + get_level + per-node loop + torch.stack +
+ *           log/abs/pow/sign epilogue  (wavelet_math.py:182-218), i.e. compute_pytorch_packet_representation.
+ *
+ *   x              device, fp32, B rows of N samples, consecutive rows x_row_stride elements apart
+ *   dec_lo_host    HOST pointer to the F low-pass decomposition taps (pywt Wavelet.dec_lo); F even, 2..64.
+ *                  The high-pass taps are derived as dec_hi[k] = (-1)^(k+1) dec_lo[F-1-k].
+ *   level          tree depth (max_lev), 1..12;  P = 2^level packets
+ *   order          AFD_ORDER_FREQ or AFD_ORDER_NATURAL (column order of the packets)
+ *   log_scale      0: raw coefficients;  1: log(|c|^power + log_offset)   (reference uses 1e-12)
+ *   sign_channel   (loss_less) with log_scale: adds channel 1 = +1 for c >= 0, -1 for c < 0
+ *   out            device, fp32, contiguous [B][C][T][P], C = 1 + (log_scale && sign_channel),
+ *                  T = afd_wpt_out_len(N, F, level).  The reference hands callers the (0,1,3,2)-permuted VIEW
+ *                  of exactly this memory (wavelet_math.py:263).
+ *   T_out          optional, receives T.
+ */
+int afd_wpt_forward(const float* x, int64_t B, int64_t N, int64_t x_row_stride,
+                    const float* dec_lo_host, int F, int level, int order,
+                    float power, int log_scale, float log_offset, int sign_channel,
+                    float* out, int64_t* T_out, void* stream);
+
+/*
+ * Same transform with HOST input and output buffers (pinned memory recommended): frames are streamed through
+ * the device in chunks with H2D copy, kernel and D2H copy overlapped on separate streams.  Blocks until `out_host`
+ * is complete.  This is the call a CPU-side user of the reference (numpy in, numpy out) would make.
+ */
+int afd_wpt_forward_host(const float* x_host, int64_t B, int64_t N, int64_t x_row_stride,
+                         const float* dec_lo_host, int F, int level, int order,
+                         float power, int log_scale, float log_offset, int sign_channel,
+                         float* out_host, int64_t* T_out, int device, int64_t chunk_frames);
+
+/*
+ * Fused STFT power spectrogram.
+ * Replaces: torchaudio.transforms.Spectrogram(n_fft, hop_length, power)(x) -> torch.stft(center=True,
+ *           pad_mode="reflect", window=hann(periodic), onesided) -> abs().pow(power), and the optional
+ *           log(spec + 1e-12)  (wavelet_math.py:47,63-66).
+ *   out   device, fp32, contiguous [B][1][frames][n_fft/2+1], frames = 1 + N / hop.  The caller exposes the
+ *         (0,1,3,2)-permuted view [B,1,bins,frames] the reference returns.
+ */
+int afd_stft_power(const float* x, int64_t B, int64_t N, int64_t x_row_stride,
+                   int n_fft, int hop, float power, int log_scale, float log_offset,
+                   float* out, void* stream);
+
+/* frames = 1 + N / hop, bins = n_fft / 2 + 1 */
+int afd_stft_out_shape(int64_t N, int n_fft, int hop, int64_t* frames, int64_t* bins);
+
+int afd_stft_power_host(const float* x_host, int64_t B, int64_t N, int64_t x_row_stride,
+                        int n_fft, int hop, float power, int log_scale, float log_offset,
+                        float* out_host, int device, int64_t chunk_frames);
+
+/*
+ * Haar wavelet-packet "fingerprint" accumulation.
+ * Replaces: pywt.WaveletPacket(clips, "haar", mode="reflect").get_level(level, order="freq") + np.stack +
+ *           np.abs + the sum part of np.mean  (scripts/freq_visual/fingerprints.py:101-115).
+ *   sums   device, DOUBLE [2^level]; sums[p] += sum over the B clips and all positions of |c_p|.
+ *   count  optional device int64 scalar; += B * T  (the number of terms behind each sum), so that
+ *          mean = sums / count also after an all-reduce(sum) of both across ranks.
+ */
+int afd_haar_fingerprint_accum(const float* x, int64_t B, int64_t N, int64_t x_row_stride, int level,
+                               double* sums, int64_t* count, void* stream);
+
+int afd_haar_fingerprint_host(const float* x_host, int64_t B, int64_t N, int64_t x_row_stride, int level,
+                              double* sums_host, int64_t* count_host, int device, int64_t chunk_frames);
+
+/*
+ * Measurement helper (bench.py): runs `iters` back-to-back launches of an FFMA-only kernel that fills every
+ * SM and returns the achieved fp32 TFLOP/s -- the live FP32-FMA roofline denominator.
+ */
+int afd_measure_fp32_fma_tflops(int iters, double* tflops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFD_B200_H */
