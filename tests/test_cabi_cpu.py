@@ -1,0 +1,81 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/afd_b200.h declares; the host-only
+entry points (shape inference, validation, error strings) behave as documented.  No compute calls here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from audiodeepfake_detection_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "afd_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(afd_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_declare_the_same_symbols():
+    assert _declared_symbols() == sorted(_lib.SIGNATURES)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    for name in _declared_symbols():
+        assert hasattr(lib, name), name
+    assert lib.afd_version() >= 100
+
+
+@pytest.mark.parametrize("N,F,level,T", [(22050, 10, 8, 95), (22050, 24, 8, 109), (22050, 16, 7, 187),
+                                          (22050, 2, 14, 2), (22050, 10, 0, 22050), (1, 2, 3, 1)])
+def test_wpt_out_len(N, F, level, T):
+    out = ctypes.c_int64(-1)
+    assert _lib.load().afd_wpt_out_len(N, F, level, ctypes.byref(out)) == 0
+    assert out.value == T
+
+
+def test_stft_out_shape():
+    lib = _lib.load()
+    frames, bins = ctypes.c_int64(), ctypes.c_int64()
+    assert lib.afd_stft_out_shape(22050, 511, 220, ctypes.byref(frames), ctypes.byref(bins)) == 0
+    assert (frames.value, bins.value) == (101, 256)
+    assert lib.afd_stft_out_shape(22050, 512, 2, ctypes.byref(frames), ctypes.byref(bins)) == 0
+    assert (frames.value, bins.value) == (11026, 257)
+
+
+def test_validation_errors_carry_a_message():
+    lib = _lib.load()
+    out = ctypes.c_int64()
+    assert lib.afd_wpt_out_len(22050, 9, 8, ctypes.byref(out)) == -1          # odd filter length
+    assert b"afd_wpt_out_len" in lib.afd_last_error()
+    assert lib.afd_wpt_out_len(0, 10, 8, ctypes.byref(out)) == -1
+    assert lib.afd_wpt_out_len(22050, 10, 8, None) == -1
+    # null pointers are rejected before any CUDA call is made
+    assert lib.afd_wpt_forward(None, 1, 22050, 22050, None, 10, 8, 0, 2.0, 1, 1e-12, 0, None, None, None) == -1
+    assert lib.afd_stft_power(None, 1, 22050, 22050, 511, 220, 2.0, 1, 1e-12, None, None) == -1
+    assert lib.afd_haar_fingerprint_accum(None, 1, 22050, 22050, 14, None, None, None) == -1
+    with pytest.raises(_lib.AfdError) as info:
+        _lib.check("afd_wpt_out_len", lib.afd_wpt_out_len(22050, 7, 8, ctypes.byref(out)))
+    assert info.value.code == -1
+
+
+def test_product_does_not_import_the_oracle():
+    """The product package must never route through oracle/ (test infrastructure only)."""
+    pkg = os.path.join(ROOT, "audiodeepfake-detection_b200")
+    for name in os.listdir(pkg):
+        if name.endswith(".py"):
+            src = open(os.path.join(pkg, name)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), name
+
+
+def test_cpu_tensors_are_rejected_not_emulated():
+    import torch
+
+    import audiodeepfake_detection_b200 as afd
+
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        afd.Packets("sym5", 8)(torch.randn(2, 1, 22050))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        afd.STFTLayer()(torch.randn(2, 1, 22050))

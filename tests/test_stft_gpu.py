@@ -1,0 +1,89 @@
+"""GPU parity of the fused STFT kernel against the reference's own code path (torchaudio Spectrogram / torch.stft
+run on the CPU), the committed golden vectors and an fp64 direct DFT."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import audiodeepfake_detection_b200 as afd
+from oracle import ptwt_like
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5        # max-norm relative on the power spectrogram (north_star: fp32 rel 1e-5)
+LOG_TOL = 1e-4    # max-norm relative after log scaling
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+def test_golden_vectors(golden_dir, golden_frames, cuda_device):
+    frames, _, _ = golden_frames
+    gold = np.load(os.path.join(golden_dir, "stft_torchaudio.npz"))
+    x = torch.from_numpy(frames[:4]).unsqueeze(1).to(cuda_device)
+    spec, aux = afd.STFTLayer(n_fft=511, hop_length=220, log_scale=False)(x)
+    assert aux is None and tuple(spec.shape) == (4, 1, 256, 101)
+    assert spec.stride() == (101 * 256, 101 * 256, 1, 256)          # [B,1,frames,bins] memory, like the DCNN wants
+    assert _rel(spec.cpu().numpy(), gold["power"]) < TOL
+    logs, _ = afd.STFTLayer(n_fft=511, hop_length=220, log_scale=True)(x)
+    truth = ptwt_like.stft_power_dft64(frames[:4])
+    want = np.log(truth + 1e-12)
+    got = logs[:, 0].cpu().numpy()
+    big = truth > 1e-6 * truth.max()
+    assert np.max(np.abs(got - want)[big]) < LOG_TOL * np.max(np.abs(want))
+    # no farther from the fp64 truth than the reference's fp32 path is (x2 slack), in aggregate
+    err_ref = np.abs(gold["log"][:, 0] - want)
+    err = np.abs(got - want)
+    for q in (50, 99, 99.9):
+        assert np.percentile(err, q) <= 2 * np.percentile(err_ref, q) + 1e-6
+
+
+@pytest.mark.parametrize("n_fft,hop,N,B", [(511, 220, 22050, 5), (512, 2, 22050, 1), (511, 220, 22051, 3),
+                                           (255, 100, 16000, 3), (64, 16, 1000, 4), (300, 1, 4000, 2),
+                                           (511, 220, 440, 2), (2, 1, 64, 2)])
+def test_matches_torch_stft(n_fft, hop, N, B, cuda_device):
+    rng = np.random.default_rng(n_fft + hop)
+    x = (rng.standard_normal((B, 1, N)) * 0.1).astype(np.float32)
+    want = ptwt_like.stft_power_explicit(torch.from_numpy(x).double(), n_fft, hop).numpy()
+    got = afd.STFTLayer(n_fft=n_fft, hop_length=hop)(torch.from_numpy(x).to(cuda_device))[0].cpu().numpy()
+    assert got.shape == want.shape
+    assert _rel(got, want) < TOL
+
+
+def test_reference_shape_kats(cuda_device):
+    """reference tests/test_transforms.py:25-51."""
+    x = torch.randn(2, 1, 22050, device=cuda_device)
+    assert tuple(afd.STFTLayer(n_fft=512, hop_length=2)(x)[0].shape) == (2, 1, 257, 11026)
+    assert tuple(afd.STFTLayer()(x)[0].shape) == (2, 1, 256, 101)
+
+
+def test_power_one_and_errors(cuda_device):
+    x = torch.randn(2, 1, 22050, device=cuda_device) * 0.1
+    mag = afd.STFTLayer(power=1.0)(x)[0]
+    pw = afd.STFTLayer(power=2.0)(x)[0]
+    assert torch.allclose(mag * mag, pw, rtol=1e-4, atol=1e-9)
+    assert afd.stft_power_features(torch.empty(0, 22050, device=cuda_device)).shape == (0, 1, 101, 256)
+    from audiodeepfake_detection_b200._lib import AfdError
+    with pytest.raises(AfdError):        # reflect padding must be smaller than the signal (torch raises too)
+        afd.stft_power_features(torch.randn(1, 200, device=cuda_device), 511, 220)
+    with pytest.raises(AfdError):
+        afd.stft_power_features(x, 2048, 512)       # outside this build's chirp-z length
+
+
+def test_parseval_full_batch(cuda_device):
+    """Size-independent property at BASELINE batch size: for the periodic Hann window at hop 220 the summed
+    one-sided power of frame f equals n * sum (w x)^2 (Parseval), checked on the device for 4096 clips."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(4096, 22050, device=cuda_device, generator=g) * 0.1
+    spec = afd.stft_power_features(x)                                   # [B,1,101,256]
+    n = 511
+    w = torch.hann_window(n, device=cuda_device)
+    xp = torch.nn.functional.pad(x.unsqueeze(1), (255, 255), mode="reflect")[:, 0]
+    seg = xp.unfold(-1, n, 220) * w                                    # [B,101,511]
+    energy = (seg.double() ** 2).sum(-1) * n
+    dc = spec[:, 0, :, 0].double()
+    total = 2 * spec[:, 0].double().sum(-1) - dc                        # odd n: every bin but DC appears twice
+    assert float(((total - energy).abs() / energy).max()) < 1e-4
+    assert torch.equal(spec, afd.stft_power_features(x))               # bitwise reproducible
