@@ -146,7 +146,7 @@ using namespace afd;
 
 extern "C" int afd_haar_fingerprint_accum(const float* x, int64_t B, int64_t N, int64_t x_row_stride, int level,
                                           double* sums, int64_t* count, void* stream) {
-    if (!x || !sums) return fail(AFD_ERR_INVALID_ARG, "afd_haar_fingerprint_accum: null pointer");
+    if (!sums || (!x && B != 0)) return fail(AFD_ERR_INVALID_ARG, "afd_haar_fingerprint_accum: null pointer");
     if (B < 0 || N < 2 || x_row_stride < N) return fail(AFD_ERR_INVALID_ARG, "afd_haar_fingerprint_accum: bad B/N/stride");
     if (level < 1 || level > kHaarMaxLevel)
         return fail(AFD_ERR_INVALID_ARG, "afd_haar_fingerprint_accum: level %d not in 1..%d", level, kHaarMaxLevel);

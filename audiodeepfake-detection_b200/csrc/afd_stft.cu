@@ -296,7 +296,7 @@ extern "C" int afd_stft_out_shape(int64_t N, int n_fft, int hop, int64_t* frames
 
 extern "C" int afd_stft_power(const float* x, int64_t B, int64_t N, int64_t x_row_stride, int n_fft, int hop,
                               float power, int log_scale, float log_offset, float* out, void* stream) {
-    if (!x || !out) return fail(AFD_ERR_INVALID_ARG, "afd_stft_power: null pointer");
+    if ((!x || !out) && B != 0) return fail(AFD_ERR_INVALID_ARG, "afd_stft_power: null pointer");
     if (B < 0 || N < 2 || x_row_stride < N || hop < 1) return fail(AFD_ERR_INVALID_ARG, "afd_stft_power: bad B/N/stride/hop");
     if (n_fft < 2) return fail(AFD_ERR_INVALID_ARG, "afd_stft_power: n_fft must be >= 2");
     if (2 * n_fft - 1 > kFftM)
