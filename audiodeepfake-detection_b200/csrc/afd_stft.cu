@@ -289,7 +289,7 @@ using namespace afd;
 
 extern "C" int afd_stft_out_shape(int64_t N, int n_fft, int hop, int64_t* frames, int64_t* bins) {
     if (N < 1 || n_fft < 2 || hop < 1 || !frames || !bins) return fail(AFD_ERR_INVALID_ARG, "afd_stft_out_shape: bad argument");
-    *frames = 1 + N / hop;
+    *frames = 1 + (N + 2 * (n_fft / 2) - n_fft) / hop;   // torch.stft(center=True): 1 + (N + 2*pad - n_fft) // hop
     *bins = n_fft / 2 + 1;
     return AFD_OK;
 }
@@ -312,7 +312,7 @@ extern "C" int afd_stft_power(const float* x, int64_t B, int64_t N, int64_t x_ro
     if (rc != AFD_OK) return rc;
     StftParams p;
     p.n_fft = n_fft; p.hop = hop; p.N = static_cast<int>(N); p.pad = n_fft / 2;
-    p.frames = static_cast<int>(1 + N / hop);
+    p.frames = static_cast<int>(1 + (N + 2 * (n_fft / 2) - n_fft) / hop);
     p.bins = n_fft / 2 + 1;
     p.pairs_per_row = (p.frames + 1) / 2;
     p.total_pairs = B * static_cast<long long>(p.pairs_per_row);

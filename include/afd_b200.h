@@ -85,14 +85,14 @@ int afd_wpt_forward_host(const float* x_host, int64_t B, int64_t N, int64_t x_ro
  * Replaces: torchaudio.transforms.Spectrogram(n_fft, hop_length, power)(x) -> torch.stft(center=True,
  *           pad_mode="reflect", window=hann(periodic), onesided) -> abs().pow(power), and the optional
  *           log(spec + 1e-12)  (wavelet_math.py:47,63-66).
- *   out   device, fp32, contiguous [B][1][frames][n_fft/2+1], frames = 1 + N / hop.  The caller exposes the
+ *   out   device, fp32, contiguous [B][1][frames][n_fft/2+1], frames = 1 + (N + 2*(n_fft/2) - n_fft) / hop.  The caller exposes the
  *         (0,1,3,2)-permuted view [B,1,bins,frames] the reference returns.
  */
 int afd_stft_power(const float* x, int64_t B, int64_t N, int64_t x_row_stride,
                    int n_fft, int hop, float power, int log_scale, float log_offset,
                    float* out, void* stream);
 
-/* frames = 1 + N / hop, bins = n_fft / 2 + 1 */
+/* frames = 1 + (N + 2*(n_fft/2) - n_fft) / hop  (torch.stft, center=True), bins = n_fft / 2 + 1 */
 int afd_stft_out_shape(int64_t N, int n_fft, int hop, int64_t* frames, int64_t* bins);
 
 int afd_stft_power_host(const float* x_host, int64_t B, int64_t N, int64_t x_row_stride,

@@ -181,7 +181,7 @@ def stft_power_dft64(x, n_fft: int = 511, hop_length: int = 220):
     x = np.asarray(x, dtype=np.float64)
     pad = n_fft // 2
     xp = np.pad(x, [(0, 0), (pad, pad)], mode="reflect")
-    frames = 1 + x.shape[-1] // hop_length
+    frames = 1 + (x.shape[-1] + 2 * pad - n_fft) // hop_length      # torch.stft(center=True)
     idx = np.arange(frames)[:, None] * hop_length + np.arange(n_fft)[None, :]
     win = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(n_fft) / n_fft)
     seg = xp[:, idx] * win                                           # [B, frames, n_fft]

@@ -43,6 +43,8 @@ def test_stft_out_shape():
     assert (frames.value, bins.value) == (101, 256)
     assert lib.afd_stft_out_shape(22050, 512, 2, ctypes.byref(frames), ctypes.byref(bins)) == 0
     assert (frames.value, bins.value) == (11026, 257)
+    assert lib.afd_stft_out_shape(16000, 255, 100, ctypes.byref(frames), ctypes.byref(bins)) == 0
+    assert (frames.value, bins.value) == (160, 128)      # odd n_fft: 1 + (N - 1) // hop, as torch.stft
 
 
 def test_validation_errors_carry_a_message():
