@@ -19,9 +19,9 @@ SIGNATURES = {
     "afd_version": (c_int, []),
     "afd_last_error": (c_char_p, []),
     "afd_wpt_out_len": (c_int, [c_int64, c_int, c_int, POINTER(c_int64)]),
-    "afd_wpt_forward": (c_int, [c_void_p, c_int64, c_int64, c_int64, POINTER(c_float), c_int, c_int, c_int,
+    "afd_wpt_forward": (c_int, [c_void_p, c_int64, c_int64, c_int64, POINTER(c_double), c_int, c_int, c_int,
                                 c_float, c_int, c_float, c_int, c_void_p, POINTER(c_int64), c_void_p]),
-    "afd_wpt_forward_host": (c_int, [c_void_p, c_int64, c_int64, c_int64, POINTER(c_float), c_int, c_int, c_int,
+    "afd_wpt_forward_host": (c_int, [c_void_p, c_int64, c_int64, c_int64, POINTER(c_double), c_int, c_int, c_int,
                                      c_float, c_int, c_float, c_int, c_void_p, POINTER(c_int64), c_int, c_int64]),
     "afd_stft_power": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_float, c_int, c_float,
                                c_void_p, c_void_p]),
@@ -32,6 +32,10 @@ SIGNATURES = {
                                            c_void_p]),
     "afd_haar_fingerprint_host": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p,
                                           c_int, c_int64]),
+    "afd_wpt_lattice_info": (c_int, [POINTER(c_double), c_int, POINTER(c_double), POINTER(c_double),
+                                     POINTER(c_double), POINTER(c_int)]),
+    "afd_wpt_plan_info": (c_int, [c_int64, POINTER(c_double), c_int, c_int, POINTER(c_int), POINTER(c_int),
+                                  POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "afd_measure_fp32_fma_tflops": (c_int, [c_int, POINTER(c_double), c_void_p]),
 }
 

@@ -11,6 +11,20 @@ namespace afd {
 constexpr int kMaxSmemPerCta = 232448;  // 227 KB opt-in limit on sm_100
 constexpr int kNumSmsFallback = 148;
 
+constexpr int kMaxLatticeStages = 32;
+
+// Paraunitary lattice of an orthogonal analysis filter pair (afd_lattice.cu).
+struct LatticeInfo {
+    int stages;                            // J = F / 2
+    int reflect0;                          // stage 0 is a reflection (det = -1): kernels fall back to the direct form
+    int usable;                            // residual, sign and dynamic range are fit for the fp32 kernels
+    double tan_theta[kMaxLatticeStages];   // stage tangents, stage 0 first
+    double scale;                          // product of the stage cosines: true = scale * unscaled lattice output
+    double residual;                       // max |tap error| of the re-synthesised filter pair
+    double max_abs_tan;
+};
+int lattice_factor(const double* dec_lo, int F, LatticeInfo* info);
+
 void set_error(const char* fmt, ...);
 int fail(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
@@ -47,10 +61,14 @@ __device__ __forceinline__ void st_cs4(float4* p, float4 v) { __stcs(p, v); }
 // power == 2 is the only value the reference's experiments use; pow(x, 2.0) is x*x exactly.
 // lg2.approx has <= 2 ulp error on the normal range; after the ln2 scale the result is within 1e-6 absolute
 // of logf on the feature range [-27.7, 10], far inside the 1e-4 parity budget.
+__device__ __forceinline__ float ln_approx(float v) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r * 0.69314718055994530942f;
+}
 __device__ __forceinline__ float log_power(float c, float power, float offset, bool square) {
-    float a = fabsf(c);
-    float pw = square ? a * a : __powf(a, power);
-    return __logf(pw + offset);
+    const float pw = square ? fmaf(c, c, offset) : __powf(fabsf(c), power) + offset;
+    return ln_approx(pw);
 }
 
 }  // namespace afd

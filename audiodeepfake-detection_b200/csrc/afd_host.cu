@@ -73,7 +73,7 @@ static int run_pipelined(const float* x_host, int64_t B, int64_t N, int64_t x_ro
 using namespace afd;
 
 extern "C" int afd_wpt_forward_host(const float* x_host, int64_t B, int64_t N, int64_t x_row_stride,
-                                    const float* dec_lo_host, int F, int level, int order, float power,
+                                    const double* dec_lo_host, int F, int level, int order, float power,
                                     int log_scale, float log_offset, int sign_channel, float* out_host,
                                     int64_t* T_out, int device, int64_t chunk_frames) {
     if (!x_host || !out_host || !dec_lo_host) return fail(AFD_ERR_INVALID_ARG, "afd_wpt_forward_host: null pointer");

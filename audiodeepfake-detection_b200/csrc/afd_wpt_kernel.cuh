@@ -1,0 +1,754 @@
+// Fused wavelet-packet analysis tree + feature epilogue for sm_100a.
+//
+// Replaces the ptwt.WaveletPacket / per-node loop / stack / log epilogue of the reference
+// (src/audiofakedetect/wavelet_math.py:182-218).  Per node the reference does
+//     x~ = reflect_pad(x, F-2 left, F-2 (+1 if len odd) right);  y[k] = sum_m h[m] * x~[2k+1-m]
+// for the low-pass h = dec_lo and the high-pass g = dec_hi, recursively to `level`, then orders the
+// leaves by Gray code, stacks them P-innermost and applies log(|c|^power + 1e-12).
+//
+// Design:
+//   * One frame is handled by TWO persistent CTAs: CTA h (0/1) owns the sub-tree under the level-1 node
+//     'a'/'d' and applies only its own level-1 filter (direct form), so no FMA is duplicated; the second read of
+//     the frame is an L2 hit.  A half-tree needs ~100 KB of shared memory for the headline configs (level 8,
+//     N = 22050), so two CTAs are resident per SM and one CTA's load / store phases overlap the other's FMAs.
+//   * Levels >= 2 evaluate the filter PAIR as a paraunitary lattice (afd_lattice.cu): J = F/2 plane rotations
+//     separated by unit delays, run in place on the register window, F FFMAs per (lo, hi) pair instead of 2F.
+//     The rotations are unscaled (u += t v', v = v' - t u); the product of the stage cosines is folded into the
+//     stores of the levels where the pending factor leaves [1e-9, 1e9] and into the epilogue of the last level.
+//     Filters whose lattice is not trustworthy (residual, reflection, F > 32) use the direct form.
+//   * Intermediate levels live in two ping-pong shared-memory regions (odd levels in A, even levels and the
+//     frame staging buffers in B).  Every node is stored WITH its reflect padding materialised (F-2 mirrored
+//     samples left, F-2 (+1) right), written by the threads that produce the mirrored coefficients.  Every
+//     work item of the next level is therefore a plain aligned window: no index reflection on the read side.
+//   * Work item = R consecutive output pairs of one node: 128-bit LDS of the 2R+F-2 window (conflict-free for
+//     R/2 odd), the FIR / lattice on registers with tap operands from the constant bank, 64-bit STS.  R is picked
+//     per level (two instantiations) so that the item count fills whole rounds of the 256 threads.
+//   * The LAST level is never stored: lanes map to consecutive parent nodes, each thread keeps its leaf
+//     coefficients in registers, applies log(c^2 + offset) and writes out[b][c][t][2q..2q+1] so that a
+//     warp covers 256 contiguous bytes of a feature row per store (frequency order: the children of natural
+//     node m sit at positions 2*igray(m) + {parity(m), 1-parity(m)}).
+//   * The frame is staged through two cp.async buffers (chunk j+1 in flight while chunk j is filtered) and the
+//     first chunk of the CTA's NEXT frame is prefetched while the last level runs.
+#pragma once
+#include <math.h>
+
+#include "afd_common.cuh"
+
+namespace afd {
+
+constexpr int kMaxLevel = 12;
+constexpr int kThreads = 256;
+constexpr int kMaxPasses = 24;
+
+template <int F>
+struct Coefs {
+    float lo[F];
+    float hi[F];
+    float t[F / 2];     // lattice stage tangents (stage 0 first)
+};
+
+// One barrier-delimited step of the half tree after level 1.
+struct Pass {
+    int kind;          // 0: stored level (shared -> shared), 1: last level (shared -> features)
+    int in_off;        // float offsets into dynamic shared memory
+    int out_off;
+    int parents;       // parent nodes handled (power of two)
+    int lg_parents;
+    int n_out;         // child node length
+    int in_stride;
+    int out_stride;
+    int rsel;          // which of the two item sizes
+    float mul;         // factor folded into the stores (1: none)
+    int parent_base;   // natural index (within the half tree) of the first parent, last level only
+    int prefetch;      // the next frame's first chunk may be staged while this pass runs
+    int sync_before;   // barrier needed before this pass even if the previous pass ended with one
+};
+
+struct WptPlan {
+    int N;                      // samples per frame
+    int L;                      // tree depth
+    int n1;                     // level-1 node length
+    int T;                      // leaf length
+    int stride1;                // padded stride of the level-1 node
+    int region_b;               // float offset of region B (region A starts at 0)
+    int buf_floats;             // floats per staging buffer (two of them at the start of region B)
+    int kc;                     // level-1 outputs per staging chunk (multiple of R1)
+    int nch;                    // staging chunks per frame
+    int npass;
+    int smem_floats;            // total dynamic shared memory in floats
+    Pass pass[kMaxPasses];
+};
+
+struct Epilogue {
+    float power;
+    float log_offset;
+    int log_scale;
+    int sign_channel;
+    int order;
+    int square;  // power == 2
+};
+
+// ------------------------------------------------------------------------------------------------
+// Direct form: R outputs (of one or both filters) from a register window.  w[j] = x~[2*k0 + 2 - F + j];
+// output r uses x~[2(k0+r)+1-m] = w[2r + F-1-m].
+// ------------------------------------------------------------------------------------------------
+template <int F, int R, int WLEN>
+__device__ __forceinline__ void fir2(const float (&w)[WLEN], const Coefs<F>& cf, float (&lo)[R], float (&hi)[R]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        float a = 0.f, d = 0.f;
+#pragma unroll
+        for (int m = 0; m < F; ++m) {
+            const float xv = w[2 * r + F - 1 - m];
+            a = fmaf(cf.lo[m], xv, a);
+            d = fmaf(cf.hi[m], xv, d);
+        }
+        lo[r] = a;
+        hi[r] = d;
+    }
+}
+
+template <int F, int R, int WLEN>
+__device__ __forceinline__ void fir1(const float (&w)[WLEN], const float (&t)[F], float (&y)[R]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        float a = 0.f;
+#pragma unroll
+        for (int m = 0; m < F; ++m) a = fmaf(t[m], w[2 * r + F - 1 - m], a);
+        y[r] = a;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lattice form, in place on the same window.  Pair i (i = 0 .. R+J-2) is p[k0-(J-1)+i] = (x~[2k+1], x~[2k])
+// = (w[2i+1], w[2i]); channel u lives in the odd slots, channel v in the even slots.
+//   stage 0:          u_i = a + t0 b,            v_i = b - t0 a
+//   stage m (1..J-1): u_i = u_i + tm v_{i-1},    v_i = v_{i-1} - tm u_i(old)       (descending i: in place)
+// After stage J-1 pairs J-1 .. R+J-2 hold (lo, hi)[k0 .. k0+R-1] / prod(cos theta_m).
+// ------------------------------------------------------------------------------------------------
+template <int F, int R, int WLEN>
+__device__ __forceinline__ void lattice2(float (&w)[WLEN], const Coefs<F>& cf, float (&lo)[R], float (&hi)[R]) {
+    constexpr int J = F / 2;
+    constexpr int NP = R + J - 1;
+    static_assert(2 * NP <= WLEN, "window too short");
+    {
+        const float t0 = cf.t[0];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            const float a = w[2 * i + 1], b = w[2 * i];
+            w[2 * i + 1] = fmaf(t0, b, a);
+            w[2 * i] = fmaf(-t0, a, b);
+        }
+    }
+#pragma unroll
+    for (int m = 1; m < J; ++m) {
+        const float tm = cf.t[m];
+#pragma unroll
+        for (int i = NP - 1; i >= m; --i) {
+            const float vd = w[2 * (i - 1)];
+            const float uo = w[2 * i + 1];
+            w[2 * i + 1] = fmaf(tm, vd, uo);
+            w[2 * i] = fmaf(-tm, uo, vd);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        lo[r] = w[2 * (J - 1 + r) + 1];
+        hi[r] = w[2 * (J - 1 + r)];
+    }
+}
+
+template <int F, int R>
+struct Win {
+    static constexpr int W = 2 * R + F - 2;   // window length
+    static constexpr int NV = (W + 3) / 4;    // float4 loads
+    static constexpr int WLEN = 4 * NV;
+};
+
+template <int NV>
+__device__ __forceinline__ void load_window(const float* __restrict__ p, float (&w)[4 * NV]) {
+    const float4* src = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const float4 q = src[v];
+        w[4 * v + 0] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
+    }
+}
+
+template <int F, int R, bool LAT>
+__device__ __forceinline__ void filter_pair(const float* __restrict__ src, const Coefs<F>& cf, float (&lo)[R],
+                                            float (&hi)[R]) {
+    using WN = Win<F, R>;
+    float w[WN::WLEN];
+    load_window<WN::NV>(src, w);
+    if constexpr (LAT) lattice2<F, R>(w, cf, lo, hi);
+    else fir2<F, R>(w, cf, lo, hi);
+}
+
+// Chunk classification of a node with n_out coefficients, stored with padl / padr mirrored samples:
+// chunk c (outputs cR .. cR+R-1) is "interior" when it holds no mirrored coefficient and is fully valid.
+struct Split {
+    int C, CL, CIe, NI, NE;
+    unsigned magicNI;     // floor(i / NI) = umulhi(i, magic) for i, NI < 2^16
+};
+__host__ __device__ inline unsigned magic_of(int d) { return d > 0 ? static_cast<unsigned>(0xFFFFFFFFu / static_cast<unsigned>(d)) + 1u : 0u; }
+
+__host__ __device__ inline Split make_split(int n_out, int R, int padl) {
+    Split s;
+    s.C = (n_out + R - 1) / R;
+    const int padr = padl + (n_out & 1);
+    int cl = padl == 0 ? 0 : padl / R + 1;
+    int cie = (n_out - 1 - padr) / R;            // chunks c < cie end before the first right-mirrored coefficient
+    if (n_out - 1 - padr < 0) cie = 0;
+    cl = cl < s.C ? cl : s.C;
+    cie = cie > cl ? cie : cl;
+    cie = cie < s.C ? cie : s.C;
+    s.CL = cl; s.CIe = cie; s.NI = cie - cl; s.NE = s.C - s.NI;
+    s.magicNI = magic_of(s.NI);
+    return s;
+}
+__device__ __forceinline__ int fast_div(int i, int d, unsigned magic) { return d == 1 ? i : static_cast<int>(__umulhi(static_cast<unsigned>(i), magic)); }
+
+template <int R>
+__device__ __forceinline__ void vec_store(float* __restrict__ dst, const float (&v)[R]) {
+    float2* d = reinterpret_cast<float2*>(dst);
+#pragma unroll
+    for (int r = 0; r < R / 2; ++r) d[r] = make_float2(v[2 * r], v[2 * r + 1]);
+}
+
+// Generic guarded store of R coefficients of a child node plus their mirror images into the node's padding.
+// `node` points at the first padding sample; coefficient k lives at node[padl + k].
+template <int R>
+__device__ __forceinline__ void edge_store(float* __restrict__ node, const float (&v)[R], int k0, int n_out, int padl) {
+    const int padr = padl + (n_out & 1);
+    float* pos = node + padl;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int k = k0 + r;
+        if (k < n_out) {
+            pos[k] = v[r];
+            if (k >= 1 && k <= padl) pos[-k] = v[r];
+            const int mr = n_out - 1 - k;
+            if (mr >= 1 && mr <= padr) pos[n_out - 1 + mr] = v[r];
+        }
+    }
+}
+
+// Left-edge chunk C (compile time) of a pair of sibling nodes: fully valid, mirrors k = 1 .. padl to -k.
+template <int R, int PADL, int C>
+__device__ __forceinline__ void left_store(float* __restrict__ plo, float* __restrict__ phi, const float (&lo)[R],
+                                           const float (&hi)[R]) {
+    vec_store<R>(plo + C * R, lo);
+    vec_store<R>(phi + C * R, hi);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int k = C * R + r;
+        if (k >= 1 && k <= PADL) {
+            plo[-k] = lo[r];
+            phi[-k] = hi[r];
+        }
+    }
+}
+
+// Right-edge chunk of a pair of sibling nodes (no left-mirrored coefficient inside): outputs k0+r are valid for
+// r <= q = n_out-1-k0 and mirrored to n_out-1+mr (mr = q - r) for 1 <= mr <= padr; one predicate pair serves both
+// channels.  plo / phi point at coefficient 0.
+template <int R>
+__device__ __forceinline__ void right_store(float* __restrict__ plo, float* __restrict__ phi, const float (&lo)[R],
+                                            const float (&hi)[R], int k0, int n_out, int padl) {
+    const int padr = padl + (n_out & 1);
+    const int q = n_out - 1 - k0;
+    float* dlo = plo + k0;
+    float* dhi = phi + k0;
+    float* mlo = plo + (n_out - 1 + q);
+    float* mhi = phi + (n_out - 1 + q);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (r <= q) { dlo[r] = lo[r]; dhi[r] = hi[r]; }
+        if (static_cast<unsigned>(q - r - 1) < static_cast<unsigned>(padr)) { mlo[-r] = lo[r]; mhi[-r] = hi[r]; }
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void scale_all(float (&lo)[R], float (&hi)[R], float mul) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) { lo[r] *= mul; hi[r] *= mul; }
+}
+
+// One stored tree level: `parents` padded nodes in `in` -> 2*parents padded nodes in `out`.
+// Interior chunks first (lanes walk along a node), then the edge chunks type-major (lanes walk across nodes).
+template <int F, int R, bool LAT>
+__device__ __forceinline__ void mid_level(const float* __restrict__ in, float* __restrict__ out, const Pass& ps,
+                                          const Coefs<F>& cf) {
+    constexpr int padl = F - 2;
+    const int n_out = ps.n_out;
+    const Split sp = make_split(n_out, R, padl);
+    const int parents = ps.parents;
+    const int n_int = parents * sp.NI;
+    const int total = parents * sp.C;
+    const bool do_mul = ps.mul != 1.0f;
+    for (int it = threadIdx.x; it < total; it += kThreads) {
+        const bool edge = it >= n_int;
+        int node, c;
+        if (!edge) {
+            node = fast_div(it, sp.NI, sp.magicNI);
+            c = sp.CL + it - node * sp.NI;
+        } else {
+            const int e = it - n_int;
+            node = e & (parents - 1);
+            const int ee = e >> ps.lg_parents;
+            c = ee < sp.CL ? ee : sp.CIe + (ee - sp.CL);
+        }
+        const int k0 = c * R;
+        float lo[R], hi[R];
+        filter_pair<F, R, LAT>(in + node * ps.in_stride + 2 * k0, cf, lo, hi);
+        if (do_mul) scale_all<R>(lo, hi, ps.mul);
+        float* d0 = out + (2 * node) * ps.out_stride;
+        float* d1 = d0 + ps.out_stride;
+        if (!edge) {
+            vec_store<R>(d0 + padl + k0, lo);
+            vec_store<R>(d1 + padl + k0, hi);
+        } else {
+            const bool left = c < sp.CL, right = c >= sp.CIe;
+            if (left && !right && c == 0) left_store<R, padl, 0>(d0 + padl, d1 + padl, lo, hi);
+            else if (left && !right && c == 1) left_store<R, padl, 1>(d0 + padl, d1 + padl, lo, hi);
+            else if (right && !left) right_store<R>(d0 + padl, d1 + padl, lo, hi, k0, n_out, padl);
+            else {
+                edge_store<R>(d0, lo, k0, n_out, padl);
+                edge_store<R>(d1, hi, k0, n_out, padl);
+            }
+        }
+    }
+}
+
+// Level 1 for one staged chunk: outputs [kb, ke) of the CTA's own filter -> padded level-1 node.
+// Sample 2*kb + 2 - F of the (reflect-extended) frame sits at buf[0].
+template <int F, int R>
+__device__ __forceinline__ void level1_chunk(const float* __restrict__ buf, float* __restrict__ node, int kb, int ke,
+                                             int n_out, const Split& sp, const float (&t)[F]) {
+    using WN = Win<F, R>;
+    constexpr int padl = F - 2;
+    const int items = (ke - kb + R - 1) / R;
+    const int c0 = kb / R;
+    for (int i = threadIdx.x; i < items; i += kThreads) {
+        const int c = c0 + i;
+        const int k0 = c * R;
+        float w[WN::WLEN];
+        load_window<WN::NV>(buf + 2 * i * R, w);
+        float y[R];
+        fir1<F, R>(w, t, y);
+        if (c >= sp.CL && c < sp.CIe) vec_store<R>(node + padl + k0, y);
+        else edge_store<R>(node, y, k0, n_out, padl);
+    }
+}
+// Chunks are cut at multiples of R, so only the last chunk (ke == n_out) holds a partial item.
+
+__device__ __forceinline__ unsigned igray(unsigned x) {
+    x ^= x >> 1; x ^= x >> 2; x ^= x >> 4; x ^= x >> 8;
+    return x;
+}
+
+// Last level: `parents` padded nodes (level L-1) -> features in global memory.  Lanes map to parents.
+template <int F, int RL, bool LAT>
+__device__ __forceinline__ void last_level(const float* __restrict__ in, const Pass& ps, int T, int half_base,
+                                           float* __restrict__ out_b, int P, const Coefs<F>& cf, const Epilogue& ep) {
+    const int parents = ps.parents;
+    const int chunks = (T + RL - 1) / RL;
+    const int total = parents * chunks;
+    const bool square = ep.square != 0;
+    const bool two = ep.log_scale && ep.sign_channel;
+    const bool do_mul = ps.mul != 1.0f;
+    const long long ch1 = static_cast<long long>(T) * P;
+    for (int it = threadIdx.x; it < total; it += kThreads) {
+        const int m = it & (parents - 1);
+        const int c = it >> ps.lg_parents;
+        const int k0 = c * RL;
+        float lo[RL], hi[RL];
+        filter_pair<F, RL, LAT>(in + m * ps.in_stride + 2 * k0, cf, lo, hi);
+        if (do_mul) scale_all<RL>(lo, hi, ps.mul);
+        const unsigned pf = static_cast<unsigned>(half_base + ps.parent_base + m);      // natural index at level L-1
+        unsigned q = pf;
+        bool swap = false;
+        if (ep.order == AFD_ORDER_FREQ) {
+            q = igray(pf);
+            swap = (q & 1u) != 0;                                      // parity(pf) = lsb of igray(pf)
+        }
+        float* o = out_b + static_cast<long long>(k0) * P + 2 * q;
+#pragma unroll
+        for (int r = 0; r < RL; ++r) {
+            if (k0 + r < T) {
+                const float c0 = swap ? hi[r] : lo[r];
+                const float c1 = swap ? lo[r] : hi[r];
+                float2 v = make_float2(c0, c1);
+                if (ep.log_scale)
+                    v = make_float2(log_power(c0, ep.power, ep.log_offset, square),
+                                    log_power(c1, ep.power, ep.log_offset, square));
+                __stcs(reinterpret_cast<float2*>(o + static_cast<long long>(r) * P), v);
+                if (two)
+                    __stcs(reinterpret_cast<float2*>(o + ch1 + static_cast<long long>(r) * P),
+                           make_float2(c0 < 0.f ? -1.f : 1.f, c1 < 0.f ? -1.f : 1.f));
+            }
+        }
+    }
+}
+
+// Stage chunk j of the frame (with the frame's own reflect padding) into `buf` with cp.async.
+template <int F>
+__device__ __forceinline__ void issue_chunk(const float* __restrict__ xg, float* __restrict__ buf, int j,
+                                            const WptPlan& plan) {
+    const int N = plan.N;
+    const int kb = j * plan.kc;
+    const int ke = min(plan.n1, kb + plan.kc);
+    const int s_start = 2 * kb + 2 - F;           // sample index stored at buf[0] (even)
+    const int s_end = 2 * ke;                     // one past the last sample any stored output needs
+    const int r_lo = max(s_start, 0);
+    const int r_hi = min(s_end, N);               // real samples [r_lo, r_hi)
+    const int tid = threadIdx.x;
+    if ((reinterpret_cast<uintptr_t>(xg) & 7) == 0) {     // r_lo is even: 8-byte copies
+        const int pairs = (r_hi - r_lo) >> 1;
+        for (int i = tid; i < pairs; i += kThreads)
+            cp_async_8(buf + (r_lo - s_start) + 2 * i, xg + r_lo + 2 * i);
+        if (((r_hi - r_lo) & 1) && tid == 0) cp_async_4(buf + (r_hi - 1 - s_start), xg + r_hi - 1);
+    } else {
+        for (int i = r_lo + tid; i < r_hi; i += kThreads) cp_async_4(buf + (i - s_start), xg + i);
+    }
+    // reflect padding of the frame itself: x~[-i] = x[i], x~[N-1+i] = x[N-1-i]
+    for (int s = s_start + tid; s < 0; s += kThreads) cp_async_4(buf + (s - s_start), xg - s);
+    for (int s = max(N, s_start) + tid; s < s_end; s += kThreads) cp_async_4(buf + (s - s_start), xg + (2 * (N - 1) - s));
+    cp_async_commit();
+}
+
+template <int F, int R1, int RA, int RB, int RLA, int RLB, bool LAT>
+__global__ void __launch_bounds__(kThreads, 2)
+wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B, float* __restrict__ out,
+                const __grid_constant__ WptPlan plan, const __grid_constant__ Coefs<F> cf,
+                const __grid_constant__ Epilogue ep) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int padl = F - 2;
+    const int L = plan.L;
+    const int half = blockIdx.x & 1;                      // gridDim.x is even: constant per CTA
+    float* const regA = smem;                              // level-1 node at its start
+    float* const regB = smem + plan.region_b;              // staging buffers at its start
+    float* const buf0 = regB;
+    float* const buf1 = regB + plan.buf_floats;
+    const int P = 1 << L;
+    const int C = (ep.log_scale && ep.sign_channel) ? 2 : 1;
+    const int T = plan.T;
+    const int n1 = plan.n1;
+    const Split sp1 = make_split(n1, R1, padl);
+    const int half_base = L >= 2 ? half << (L - 2) : 0;   // natural index of the half tree's first level-(L-1) node
+    // the CTA's level-1 filter
+    float t1[F];
+#pragma unroll
+    for (int m = 0; m < F; ++m) t1[m] = half ? cf.hi[m] : cf.lo[m];
+    bool prefetched = false;
+    bool first = true;
+
+    for (long long wk = blockIdx.x; wk < 2 * B; wk += gridDim.x) {
+        const long long b = wk >> 1;
+        const float* xg = x + b * x_row_stride;
+        const long long nb = wk + gridDim.x;
+        if (!prefetched) {
+            if (!first) __syncthreads();                   // region B may still be read by the previous last level
+            issue_chunk<F>(xg, buf0, 0, plan);
+        }
+        first = false;
+        prefetched = false;
+        // ---------------------------------------------------------------- level 1 (frame -> own padded node in A)
+        for (int j = 0; j < plan.nch; ++j) {
+            cp_async_wait<0>();
+            __syncthreads();
+            if (j + 1 < plan.nch) issue_chunk<F>(xg, ((j + 1) & 1) ? buf1 : buf0, j + 1, plan);
+            const int kb = j * plan.kc;
+            const int ke = min(n1, kb + plan.kc);
+            level1_chunk<F, R1>((j & 1) ? buf1 : buf0, regA, kb, ke, n1, sp1, t1);
+        }
+        __syncthreads();
+        float* out_b = out + b * C * static_cast<long long>(T) * P;
+        if (L == 1) {
+            // the level-1 node is the output: epilogue straight from shared memory (rare configuration)
+            if (nb < 2 * B) { issue_chunk<F>(x + (nb >> 1) * x_row_stride, buf0, 0, plan); prefetched = true; }
+            const bool square = ep.square != 0;
+            for (int e = threadIdx.x; e < T; e += kThreads) {
+                const float c = regA[padl + e];
+                float* dst = out_b + static_cast<long long>(e) * P + half;
+                if (ep.log_scale) {
+                    st_cs(dst, log_power(c, ep.power, ep.log_offset, square));
+                    if (C == 2) st_cs(dst + static_cast<long long>(T) * P, c < 0.f ? -1.f : 1.f);
+                } else {
+                    st_cs(dst, c);
+                }
+            }
+            continue;
+        }
+        // ---------------------------------------------------------------- levels 2 .. L as planned passes
+        for (int pi = 0; pi < plan.npass; ++pi) {
+            const Pass& ps = plan.pass[pi];
+            if (ps.sync_before) __syncthreads();
+            if (ps.kind == 0) {
+                if (ps.rsel == 0) mid_level<F, RA, LAT>(smem + ps.in_off, smem + ps.out_off, ps, cf);
+                else mid_level<F, RB, LAT>(smem + ps.in_off, smem + ps.out_off, ps, cf);
+                __syncthreads();
+            } else {
+                if (ps.prefetch && nb < 2 * B) {
+                    issue_chunk<F>(x + (nb >> 1) * x_row_stride, buf0, 0, plan);
+                    prefetched = true;
+                }
+                if (ps.rsel == 0) last_level<F, RLA, LAT>(smem + ps.in_off, ps, T, half_base, out_b, P, cf, ep);
+                else last_level<F, RLB, LAT>(smem + ps.in_off, ps, T, half_base, out_b, P, cf, ep);
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+struct Tuning {
+    int R1, RA, RB, RLA, RLB;
+    bool lat;
+    double halo;      // extra pairs per item a lattice item pays: (J-1)/2; 0 for the direct form
+};
+
+// items * per-item cost in units of one output pair (lattice: R + (J-1)/2 rotations-columns; direct: R)
+static double level_cost(int nodes, int n_out, int R, double halo) {
+    const long long items = static_cast<long long>(nodes) * ((n_out + R - 1) / R);
+    const long long rounds = (items + kThreads - 1) / kThreads;
+    return static_cast<double>(rounds) * (R + halo);
+}
+
+// Builds the shared-memory plan and the pass list for `ctas_per_sm` resident CTAs.
+static int make_plan(int64_t N, int F, int L, const Tuning& tu, int ctas_per_sm, double level_scale, WptPlan* p,
+                     int shave_bytes = 0) {
+    int n[kMaxLevel + 1], stride[kMaxLevel + 1];
+    p->N = static_cast<int>(N);
+    p->L = L;
+    n[0] = static_cast<int>(N);
+    for (int l = 1; l <= L; ++l) n[l] = (n[l - 1] + F - 1) / 2;
+    for (int l = 0; l < L; ++l)
+        if (n[l] < F - 1 + (n[l] & 1) || n[l] < 2)
+            return fail(AFD_ERR_REFLECT_PAD,
+                        "node length %d at level %d is not longer than the reflect padding of a %d-tap filter",
+                        n[l], l, F);
+    p->n1 = n[1];
+    p->T = n[L];
+    const int padl = F - 2;
+    const int limit_floats = ((ctas_per_sm == 2 ? (228 * 1024 / 2 - 1024) : kMaxSmemPerCta) - shave_bytes) / 4;
+    int maxR = tu.R1;
+    for (int r : {tu.RA, tu.RB, tu.RLA, tu.RLB}) maxR = r > maxR ? r : maxR;
+    const int tail = round_up(2 * maxR + 1, 4);               // over-read slack behind the last node of a region:
+                                                              // the last item's window ends <= 2R+1 floats past its node
+    const int stored = L == 1 ? 1 : L - 1;                    // levels kept in shared memory
+    for (int l = 1; l <= stored; ++l) {
+        int s = round_up(n[l] + 2 * padl + (n[l] & 1), 4);
+        if (l >= 2 && ((s >> 2) & 1) == 0) s += 4;            // lanes walk across nodes in edge / last-level items: odd 16-byte stride
+        stride[l] = s;
+    }
+    p->stride1 = stride[1];
+    // level-1 staging: balanced chunks of at most kThreads items
+    const int n1 = n[1];
+    p->nch = (n1 + kThreads * tu.R1 - 1) / (kThreads * tu.R1);
+    p->kc = round_up((n1 + p->nch - 1) / p->nch, tu.R1);
+    p->nch = (n1 + p->kc - 1) / p->kc;
+    p->buf_floats = round_up(2 * p->kc + F + 8, 4);
+    int G = 1;
+    int need[2];
+    for (;; G *= 2) {
+        if (G > 4 || (G > 1 && (L < 4 || (1 << (L - 2)) / G < 2))) return AFD_ERR_UNSUPPORTED;   // caller retries / reports
+        need[0] = 0; need[1] = 2 * p->buf_floats;             // [0] = region A (odd levels), [1] = region B
+        for (int l = 1; l <= stored; ++l) {
+            int nodes = 1 << (l - 1);
+            if (l == L - 1 && G > 1) nodes /= G;
+            const int fl = nodes * stride[l] + tail;
+            int& r = need[(l & 1) ? 0 : 1];
+            r = r > fl ? r : fl;
+        }
+        p->region_b = round_up(need[0], 4);
+        p->smem_floats = p->region_b + round_up(need[1], 4);
+        if (p->smem_floats <= limit_floats) break;
+    }
+    if (L == 1) { p->npass = 0; return AFD_OK; }
+    // ---- pass list.  `pending`: true coefficient = pending * stored value (the unscaled lattice defers its cosines)
+    auto region = [&](int l) { return (l & 1) ? 0 : p->region_b; };
+    double pending = 1.0;
+    int np = 0;
+    auto pick = [&](int nodes, int n_out, int ra, int rb) {
+        return level_cost(nodes, n_out, rb, tu.halo) < level_cost(nodes, n_out, ra, tu.halo) ? 1 : 0;
+    };
+    auto stored_mul = [&]() {                                 // factor for a stored level
+        if (!tu.lat) return 1.0f;
+        pending *= level_scale;
+        if (fabs(pending) < 1e-9 || fabs(pending) > 1e9) { const float m = static_cast<float>(pending); pending = 1.0; return m; }
+        return 1.0f;
+    };
+    const int last_full = G > 1 ? L - 2 : L - 1;
+    for (int l = 2; l <= last_full; ++l) {
+        Pass& ps = p->pass[np++];
+        ps = Pass{};
+        ps.kind = 0; ps.in_off = region(l - 1); ps.out_off = region(l);
+        ps.parents = 1 << (l - 2); ps.lg_parents = l - 2; ps.n_out = n[l];
+        ps.in_stride = stride[l - 1]; ps.out_stride = stride[l];
+        ps.rsel = pick(ps.parents, ps.n_out, tu.RA, tu.RB);
+        ps.mul = stored_mul();
+    }
+    const int nodes_lm1 = 1 << (L - 2);                       // level L-1 nodes of this half tree
+    const int per_group = nodes_lm1 / G;
+    float grouped_mul = 1.0f;
+    if (G > 1) grouped_mul = stored_mul();                    // same factor for every slice of level L-1
+    const float last_mul = tu.lat ? static_cast<float>(pending * level_scale) : 1.0f;
+    const bool can_prefetch = ((L - 1) & 1) == 1;             // region B is idle while the last level reads region A
+    for (int g = 0; g < G; ++g) {
+        if (G > 1) {
+            Pass& ps = p->pass[np++];
+            ps = Pass{};
+            const int par = per_group / 2;                    // level L-2 parents of this slice
+            ps.kind = 0; ps.in_off = region(L - 2) + g * par * stride[L - 2]; ps.out_off = region(L - 1);
+            ps.parents = par; ps.lg_parents = ilog2(par); ps.n_out = n[L - 1];
+            ps.in_stride = stride[L - 2]; ps.out_stride = stride[L - 1];
+            ps.rsel = pick(par, ps.n_out, tu.RA, tu.RB);
+            ps.mul = grouped_mul;
+            ps.sync_before = g > 0;                           // the level L-1 slice is being re-used
+        }
+        Pass& ps = p->pass[np++];
+        ps = Pass{};
+        ps.kind = 1; ps.in_off = region(L - 1);
+        ps.parents = per_group; ps.lg_parents = ilog2(per_group); ps.n_out = n[L];
+        ps.in_stride = stride[L - 1];
+        ps.rsel = pick(per_group, n[L], tu.RLA, tu.RLB);
+        ps.mul = last_mul;
+        ps.parent_base = g * per_group;
+        ps.prefetch = (g == G - 1 && can_prefetch) ? 1 : 0;
+    }
+    p->npass = np;
+    return AFD_OK;
+}
+
+// What afd_wpt_plan_info reports (host-side introspection of the launch configuration).
+struct PlanReport {
+    int smem_bytes, ctas_per_sm, lattice, passes, nch, kc;
+    int pass_items[kMaxPasses];      // work items of each pass
+    int pass_r[kMaxPasses];          // item size chosen for each pass
+};
+
+template <int F, int R1, int RA, int RB, int RLA, int RLB, bool LAT>
+static int launch(const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* out, int L,
+                  const double* dec_lo, const LatticeInfo& lat, const Epilogue& ep, cudaStream_t stream,
+                  PlanReport* report) {
+    WptPlan plan;
+    Tuning tu{R1, RA, RB, RLA, RLB, LAT, LAT ? (F / 2 - 1) * 0.5 : 0.0};
+    int ctas = 2;
+    int rc = make_plan(N, F, L, tu, 2, lat.scale, &plan);
+    if (rc == AFD_ERR_UNSUPPORTED) {
+        ctas = 1;
+        rc = make_plan(N, F, L, tu, 1, lat.scale, &plan);
+        if (rc == AFD_ERR_UNSUPPORTED)
+            return fail(AFD_ERR_UNSUPPORTED,
+                        "wavelet-packet tree (N=%lld, F=%d, level=%d) needs %lld bytes of shared memory per CTA, limit %d",
+                        static_cast<long long>(N), F, L, 4LL * plan.smem_floats, kMaxSmemPerCta);
+    }
+    if (rc != AFD_OK) return rc;
+    if (report) {
+        report->smem_bytes = 4 * plan.smem_floats; report->ctas_per_sm = ctas; report->lattice = LAT ? 1 : 0;
+        report->passes = plan.npass; report->nch = plan.nch; report->kc = plan.kc;
+        for (int i = 0; i < plan.npass; ++i) {
+            const Pass& ps = plan.pass[i];
+            const int r = ps.kind == 0 ? (ps.rsel ? RB : RA) : (ps.rsel ? RLB : RLA);
+            report->pass_r[i] = r;
+            report->pass_items[i] = ps.parents * ((ps.n_out + r - 1) / r);
+        }
+        return AFD_OK;
+    }
+    Coefs<F> cf;
+    for (int k = 0; k < F; ++k) {
+        cf.lo[k] = static_cast<float>(dec_lo[k]);
+        cf.hi[k] = static_cast<float>(((k & 1) ? 1.0 : -1.0) * dec_lo[F - 1 - k]);   // dec_hi[k] = (-1)^(k+1) dec_lo[F-1-k]
+    }
+    for (int m = 0; m < F / 2; ++m) cf.t[m] = LAT ? static_cast<float>(lat.tan_theta[m]) : 0.f;
+    auto kern = wpt_tree_kernel<F, R1, RA, RB, RLA, RLB, LAT>;
+    static thread_local bool configured[16] = {false};  // per device
+    int dev = 0, sms = kNumSmsFallback;
+    AFD_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 16 || !configured[dev]) {
+        AFD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta));
+        AFD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cudaSharedmemCarveoutMaxShared));
+        if (dev < 16) configured[dev] = true;
+    }
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (ctas == 2) {
+        // the plan may sit exactly on the two-CTAs-per-SM boundary: if the driver disagrees, re-plan with head-room
+        int resident = 0;
+        AFD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kThreads, 4 * plan.smem_floats));
+        if (resident < 2 && make_plan(N, F, L, tu, 2, lat.scale, &plan, 4096) != AFD_OK) {
+            ctas = 1;
+            rc = make_plan(N, F, L, tu, 1, lat.scale, &plan);
+            if (rc != AFD_OK) return rc;
+        }
+    }
+    const int smem = 4 * plan.smem_floats;
+    long long grid = 2LL * sms * ctas / 2 * 2;             // persistent: every resident slot, even count
+    if (ctas == 1) grid = sms / 2 * 2;
+    if (grid > 2 * B) grid = 2 * B;
+    kern<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(x, static_cast<long long>(x_row_stride),
+                                                                   static_cast<long long>(B), out, plan, cf, ep);
+    AFD_CUDA_TRY(cudaGetLastError());
+    return AFD_OK;
+}
+
+// Item sizes.  R/2 odd keeps the 128-bit window loads and 64-bit stores of consecutive lanes conflict-free; larger
+// R amortises the F-2 halo (and, for the lattice, its (J-1)/2 extra rotation columns), smaller R bounds the
+// register window of 2R+F-2 floats.  Two sizes per kernel let the plan fill whole rounds of 256 threads.
+constexpr int pick_r1(int F) { return F <= 24 ? 14 : (F <= 40 ? 10 : 6); }
+constexpr int pick_rd(int F) { return F <= 40 ? 10 : 6; }           // direct form, F > 32
+// second last-level item size: a quarter of the leaf length of the headline shape (N = 22050, level 8: T ~ 85 + F)
+constexpr int pick_rlb(int F) { return 2 * ((85 + F + 7) / 8); }
+
+template <int F>
+static int dispatch_one(const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* out, int L,
+                        const double* dec_lo, const Epilogue& ep, cudaStream_t stream, PlanReport* report) {
+    LatticeInfo lat{};
+    lat.scale = 1.0;
+    if constexpr (F <= 32) {
+        if (lattice_factor(dec_lo, F, &lat) == AFD_OK && lat.usable)
+            return launch<F, pick_r1(F), 22, 30, 14, pick_rlb(F), true>(x, B, N, x_row_stride, out, L, dec_lo, lat, ep, stream, report);
+        return launch<F, pick_r1(F), 14, 10, 14, 10, false>(x, B, N, x_row_stride, out, L, dec_lo, lat, ep, stream, report);
+    } else {
+        return launch<F, pick_r1(F), pick_rd(F), pick_rd(F), pick_rd(F), pick_rd(F), false>(
+            x, B, N, x_row_stride, out, L, dec_lo, lat, ep, stream, report);
+    }
+}
+
+
+// Filter lengths are compiled in four groups (separate translation units, built in parallel).
+using WptGroupFn = int (*)(int F, const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* out, int L,
+                           const double* dec_lo, const Epilogue& ep, cudaStream_t stream, PlanReport* report);
+int wpt_group0(int F, const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* out, int L,
+               const double* dec_lo, const Epilogue& ep, cudaStream_t stream, PlanReport* report);   // F = 2 .. 16
+int wpt_group1(int F, const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* out, int L,
+               const double* dec_lo, const Epilogue& ep, cudaStream_t stream, PlanReport* report);   // F = 18 .. 32
+int wpt_group2(int F, const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* out, int L,
+               const double* dec_lo, const Epilogue& ep, cudaStream_t stream, PlanReport* report);   // F = 34 .. 48
+int wpt_group3(int F, const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* out, int L,
+               const double* dec_lo, const Epilogue& ep, cudaStream_t stream, PlanReport* report);   // F = 50 .. 64
+
+#define AFD_WPT_GROUP(NAME, F0)                                                                                      \
+    int NAME(int F, const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* out, int L,                   \
+             const double* dec_lo, const Epilogue& ep, cudaStream_t stream, PlanReport* report) {                    \
+        switch (F) {                                                                                                 \
+            case F0: return dispatch_one<F0>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report);             \
+            case F0 + 2: return dispatch_one<F0 + 2>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report);     \
+            case F0 + 4: return dispatch_one<F0 + 4>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report);     \
+            case F0 + 6: return dispatch_one<F0 + 6>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report);     \
+            case F0 + 8: return dispatch_one<F0 + 8>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report);     \
+            case F0 + 10: return dispatch_one<F0 + 10>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report);   \
+            case F0 + 12: return dispatch_one<F0 + 12>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report);   \
+            case F0 + 14: return dispatch_one<F0 + 14>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report);   \
+        }                                                                                                            \
+        return fail(AFD_ERR_INVALID_ARG, "unsupported filter length %d", F);                                         \
+    }
+
+}  // namespace afd

@@ -68,7 +68,7 @@ def wavelet_packet_features(pt_data: torch.Tensor, wavelet, max_lev: int = 8, lo
     C = 2 if (log_scale and loss_less) else 1
     P = 1 << max_lev
     out = torch.empty((B, C, T, P), dtype=torch.float32, device=x.device)
-    c_taps = (ctypes.c_float * F)(*taps)
+    c_taps = (ctypes.c_double * F)(*taps)
     with torch.cuda.device(x.device):
         rc = _lib.load().afd_wpt_forward(
             ctypes.c_void_p(x.data_ptr()), B, N, x.stride(0) if B > 1 else N, c_taps, F, max_lev,

@@ -324,7 +324,7 @@ def main():
         if kind == "packets":
             T = afd.wpt_out_len(N_SAMPLES, len(wav.dec_lo), level)
             oh = torch.empty(B, 1, T, 1 << level, dtype=torch.float32).pin_memory()
-            taps = (ctypes.c_float * len(wav.dec_lo))(*wav.dec_lo)
+            taps = (ctypes.c_double * len(wav.dec_lo))(*wav.dec_lo)
 
             def host_step():
                 _lib.check("afd_wpt_forward_host", lib.afd_wpt_forward_host(

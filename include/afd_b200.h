@@ -54,7 +54,8 @@ int afd_wpt_out_len(int64_t N, int F, int level, int64_t* T_out);
  *           log/abs/pow/sign epilogue  (wavelet_math.py:182-218), i.e. compute_pytorch_packet_representation.
  *
  *   x              device, fp32, B rows of N samples, consecutive rows x_row_stride elements apart
- *   dec_lo_host    HOST pointer to the F low-pass decomposition taps (pywt Wavelet.dec_lo); F even, 2..64.
+ *   dec_lo_host    HOST pointer to the F low-pass decomposition taps in double precision, as
+ *                  pywt.Wavelet(name).dec_lo holds them (wavelet_math.py:239); F even, 2..64.
  *                  The high-pass taps are derived as dec_hi[k] = (-1)^(k+1) dec_lo[F-1-k].
  *   level          tree depth (max_lev), 1..12;  P = 2^level packets
  *   order          AFD_ORDER_FREQ or AFD_ORDER_NATURAL (column order of the packets)
@@ -66,7 +67,7 @@ int afd_wpt_out_len(int64_t N, int F, int level, int64_t* T_out);
  *   T_out          optional, receives T.
  */
 int afd_wpt_forward(const float* x, int64_t B, int64_t N, int64_t x_row_stride,
-                    const float* dec_lo_host, int F, int level, int order,
+                    const double* dec_lo_host, int F, int level, int order,
                     float power, int log_scale, float log_offset, int sign_channel,
                     float* out, int64_t* T_out, void* stream);
 
@@ -76,7 +77,7 @@ int afd_wpt_forward(const float* x, int64_t B, int64_t N, int64_t x_row_stride,
  * is complete.  This is the call a CPU-side user of the reference (numpy in, numpy out) would make.
  */
 int afd_wpt_forward_host(const float* x_host, int64_t B, int64_t N, int64_t x_row_stride,
-                         const float* dec_lo_host, int F, int level, int order,
+                         const double* dec_lo_host, int F, int level, int order,
                          float power, int log_scale, float log_offset, int sign_channel,
                          float* out_host, int64_t* T_out, int device, int64_t chunk_frames);
 
@@ -112,6 +113,23 @@ int afd_haar_fingerprint_accum(const float* x, int64_t B, int64_t N, int64_t x_r
 
 int afd_haar_fingerprint_host(const float* x_host, int64_t B, int64_t N, int64_t x_row_stride, int level,
                               double* sums_host, int64_t* count_host, int device, int64_t chunk_frames);
+
+/*
+ * Diagnostic: the paraunitary lattice (plane rotations + unit delays) the wavelet-packet kernel evaluates instead
+ * of the direct-form filter pair when `usable` is 1 -- half the multiplies per coefficient pair.  tan_theta
+ * receives F/2 stage tangents (stage 0 first), scale the product of the stage cosines, residual the largest
+ * |tap error| of the re-synthesised filter pair against dec_lo / dec_hi.  Host only; no device work.
+ */
+int afd_wpt_lattice_info(const double* dec_lo_host, int F, double* tan_theta, double* scale,
+                         double* residual, int* usable);
+
+/*
+ * Diagnostic: the launch configuration afd_wpt_forward would use for (N, taps, level): dynamic shared memory per
+ * CTA, resident CTAs per SM, whether the lattice path is taken, and per barrier-delimited pass after level 1 the
+ * number of work items and the item size.  pass_items / pass_r must hold 24 ints.  Host only; no device work.
+ */
+int afd_wpt_plan_info(int64_t N, const double* dec_lo_host, int F, int level, int* smem_bytes, int* ctas_per_sm,
+                      int* lattice, int* passes, int* pass_items, int* pass_r);
 
 /*
  * Measurement helper (bench.py): runs `iters` back-to-back launches of an FFMA-only kernel that fills every

@@ -81,3 +81,59 @@ def test_cpu_tensors_are_rejected_not_emulated():
         afd.Packets("sym5", 8)(torch.randn(2, 1, 22050))
     with pytest.raises(RuntimeError, match="no CPU path"):
         afd.STFTLayer()(torch.randn(2, 1, 22050))
+
+
+def _lattice_resynth(tans, scale):
+    """Taps of the filter pair the kernels' rotation chain evaluates: E(z) = R_{J-1} L(z) ... L(z) R_0 with
+    R_m = cos(theta_m) [[1, t_m], [-t_m, 1]] and L(z) delaying the second channel by one pair."""
+    import numpy as np
+
+    blocks = [np.array([[1.0, tans[0]], [-tans[0], 1.0]])]
+    for t in tans[1:]:
+        nxt = [np.zeros((2, 2)) for _ in range(len(blocks) + 1)]
+        for j, blk in enumerate(blocks):
+            nxt[j][0] += blk[0]
+            nxt[j + 1][1] += blk[1]
+        rot = np.array([[1.0, t], [-t, 1.0]])
+        blocks = [rot @ blk for blk in nxt]
+    lo = np.concatenate([blk[0] for blk in blocks]) * scale
+    hi = np.concatenate([blk[1] for blk in blocks]) * scale
+    return lo, hi
+
+
+@pytest.mark.parametrize("name", ["haar", "db2", "sym5", "db8", "coif4", "sym8", "coif3", "db16"])
+def test_lattice_factorisation_reproduces_the_filter_pair(name):
+    """The paraunitary lattice the packet kernel evaluates (half the multiplies of the direct form) must be the
+    same filter pair: re-synthesise dec_lo / dec_hi from the reported stage tangents."""
+    import numpy as np
+
+    from oracle.filters import dec_hi
+    from audiodeepfake_detection_b200.wavelets import Wavelet
+
+    taps = np.asarray(Wavelet(name).dec_lo, dtype=np.float64)
+    F = len(taps)
+    c_taps = (ctypes.c_double * F)(*taps)
+    tans = (ctypes.c_double * 32)()
+    scale, resid, usable = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+    lib = _lib.load()
+    assert lib.afd_wpt_lattice_info(c_taps, F, tans, ctypes.byref(scale), ctypes.byref(resid), ctypes.byref(usable)) == 0
+    assert usable.value == 1 and resid.value < 2e-9
+    lo, hi = _lattice_resynth(list(tans)[:F // 2], scale.value)
+    assert np.max(np.abs(lo - taps)) < 2e-9
+    assert np.max(np.abs(hi - np.asarray(dec_hi(taps)))) < 2e-9
+
+
+def test_plan_info_headline_shapes_fit_two_ctas_per_sm():
+    from audiodeepfake_detection_b200.wavelets import Wavelet
+
+    lib = _lib.load()
+    for name in ("sym5", "coif4"):
+        taps = Wavelet(name).dec_lo
+        c_taps = (ctypes.c_double * len(taps))(*taps)
+        smem, ctas, lat, npass = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        items, rs = (ctypes.c_int * 24)(), (ctypes.c_int * 24)()
+        assert lib.afd_wpt_plan_info(22050, c_taps, len(taps), 8, ctypes.byref(smem), ctypes.byref(ctas),
+                                     ctypes.byref(lat), ctypes.byref(npass), items, rs) == 0
+        assert ctas.value == 2 and lat.value == 1 and smem.value <= 115712
+        assert npass.value == 7                                     # levels 2..8, no slicing of level 7
+        assert all(0 < items[i] <= 256 for i in range(npass.value))  # one round of the 256 threads per level

@@ -91,7 +91,7 @@ def test_host_buffer_api_matches_device_api(B, chunk, cuda_device):
     rng = np.random.default_rng(B)
     x = np.ascontiguousarray((rng.standard_normal((B, 22050)) * 0.1).astype(np.float32))
     taps = afd.Wavelet("sym5").dec_lo
-    c_taps = (ctypes.c_float * 10)(*taps)
+    c_taps = (ctypes.c_double * 10)(*taps)
     out = np.empty((B, 1, 95, 256), dtype=np.float32)
     T = ctypes.c_int64()
     rc = lib.afd_wpt_forward_host(x.ctypes.data, B, 22050, 22050, c_taps, 10, 8, 0, 2.0, 1, 1e-12, 0, out.ctypes.data,

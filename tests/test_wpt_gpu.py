@@ -79,7 +79,9 @@ def test_sign_channel_and_natural_order():
 
 @pytest.mark.parametrize("N,level,name", [(22050, 1, "sym5"), (22050, 2, "coif4"), (22050, 3, "db4"), (16000, 8, "sym5"),
                                           (22051, 8, "sym5"), (4097, 5, "db3"), (333, 3, "coif1"), (64, 2, "db2"),
-                                          (22050, 10, "db4"), (22050, 9, "sym5")])
+                                          (22050, 10, "db4"), (22050, 9, "sym5"), (40, 3, "coif4"), (24, 2, "sym5"),
+                                          (22050, 8, "db10"), (22050, 8, "db18"), (22050, 8, "db20"), (22050, 6, "haar"),
+                                          (30000, 8, "coif3"), (8000, 7, "sym8")])
 def test_ragged_shapes(N, level, name):
     rng = np.random.default_rng(4)
     x = rng.standard_normal((3, N)).astype(np.float32)
@@ -113,7 +115,7 @@ def test_empty_batch_and_errors(cuda_device):
     assert out.shape == (0, 1, 95, 256)
     from audiodeepfake_detection_b200._lib import AfdError
     with pytest.raises(AfdError):   # node shorter than the reflect padding (torch F.pad raises in the reference)
-        afd.wavelet_packet_features(torch.randn(1, 40, device=cuda_device), Wavelet("coif4"), 3)
+        afd.wavelet_packet_features(torch.randn(1, 20, device=cuda_device), Wavelet("coif4"), 3)
     with pytest.raises(RuntimeError):
         afd.wavelet_packet_features(torch.randn(1, 22050), Wavelet("sym5"), 8)   # CPU tensor: no fallback
 
