@@ -189,6 +189,7 @@ __device__ __forceinline__ void filter_pair(const float* __restrict__ src, const
 // chunk c (outputs cR .. cR+R-1) is "interior" when it holds no mirrored coefficient and is fully valid.
 struct Split {
     int C, CL, CIe, NI, NE;
+    int CR;               // first chunk holding a right-mirrored or invalid coefficient (unclamped CIe)
     unsigned magicNI;     // floor(i / NI) = umulhi(i, magic) for i, NI < 2^16
 };
 __host__ __device__ inline unsigned magic_of(int d) { return d > 0 ? static_cast<unsigned>(0xFFFFFFFFu / static_cast<unsigned>(d)) + 1u : 0u; }
@@ -200,6 +201,7 @@ __host__ __device__ inline Split make_split(int n_out, int R, int padl) {
     int cl = padl == 0 ? 0 : padl / R + 1;
     int cie = (n_out - 1 - padr) / R;            // chunks c < cie end before the first right-mirrored coefficient
     if (n_out - 1 - padr < 0) cie = 0;
+    s.CR = cie;
     cl = cl < s.C ? cl : s.C;
     cie = cie > cl ? cie : cl;
     cie = cie < s.C ? cie : s.C;
@@ -262,11 +264,17 @@ __device__ __forceinline__ void right_store(float* __restrict__ plo, float* __re
     float* dhi = phi + k0;
     float* mlo = plo + (n_out - 1 + q);
     float* mhi = phi + (n_out - 1 + q);
+    if (q >= R - 1) {                      // every coefficient of the chunk exists
+        vec_store<R>(dlo, lo);
+        vec_store<R>(dhi, hi);
+    } else {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        if (r <= q) { dlo[r] = lo[r]; dhi[r] = hi[r]; }
-        if (static_cast<unsigned>(q - r - 1) < static_cast<unsigned>(padr)) { mlo[-r] = lo[r]; mhi[-r] = hi[r]; }
+        for (int r = 0; r < R; ++r)
+            if (r <= q) { dlo[r] = lo[r]; dhi[r] = hi[r]; }
     }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+        if (static_cast<unsigned>(q - r - 1) < static_cast<unsigned>(padr)) { mlo[-r] = lo[r]; mhi[-r] = hi[r]; }
 }
 
 template <int R>
@@ -309,7 +317,7 @@ __device__ __forceinline__ void mid_level(const float* __restrict__ in, float* _
             vec_store<R>(d0 + padl + k0, lo);
             vec_store<R>(d1 + padl + k0, hi);
         } else {
-            const bool left = c < sp.CL, right = c >= sp.CIe;
+            const bool left = c < sp.CL, right = c >= sp.CR;
             if (left && !right && c == 0) left_store<R, padl, 0>(d0 + padl, d1 + padl, lo, hi);
             else if (left && !right && c == 1) left_store<R, padl, 1>(d0 + padl, d1 + padl, lo, hi);
             else if (right && !left) right_store<R>(d0 + padl, d1 + padl, lo, hi, k0, n_out, padl);
@@ -355,9 +363,10 @@ __device__ __forceinline__ void last_level(const float* __restrict__ in, const P
     const int parents = ps.parents;
     const int chunks = (T + RL - 1) / RL;
     const int total = parents * chunks;
-    const bool square = ep.square != 0;
     const bool two = ep.log_scale && ep.sign_channel;
     const bool do_mul = ps.mul != 1.0f;
+    const int mode = !ep.log_scale ? 0 : (ep.square ? 1 : 2);    // 0 raw, 1 log(c^2 + off), 2 log(|c|^p + off)
+    const float off = ep.log_offset;
     const long long ch1 = static_cast<long long>(T) * P;
     for (int it = threadIdx.x; it < total; it += kThreads) {
         const int m = it & (parents - 1);
@@ -373,22 +382,31 @@ __device__ __forceinline__ void last_level(const float* __restrict__ in, const P
             q = igray(pf);
             swap = (q & 1u) != 0;                                      // parity(pf) = lsb of igray(pf)
         }
-        float* o = out_b + static_cast<long long>(k0) * P + 2 * q;
+        // children of natural node m sit at columns 2q + {0, 1}; `swap` exchanges them: resolved by addressing
+        float* o_lo = out_b + static_cast<long long>(k0) * P + 2 * q + (swap ? 1 : 0);
+        float* o_hi = out_b + static_cast<long long>(k0) * P + 2 * q + (swap ? 0 : 1);
+        const int nv = T - k0;                                         // rows r < nv exist
+        if (two) {
 #pragma unroll
-        for (int r = 0; r < RL; ++r) {
-            if (k0 + r < T) {
-                const float c0 = swap ? hi[r] : lo[r];
-                const float c1 = swap ? lo[r] : hi[r];
-                float2 v = make_float2(c0, c1);
-                if (ep.log_scale)
-                    v = make_float2(log_power(c0, ep.power, ep.log_offset, square),
-                                    log_power(c1, ep.power, ep.log_offset, square));
-                __stcs(reinterpret_cast<float2*>(o + static_cast<long long>(r) * P), v);
-                if (two)
-                    __stcs(reinterpret_cast<float2*>(o + ch1 + static_cast<long long>(r) * P),
-                           make_float2(c0 < 0.f ? -1.f : 1.f, c1 < 0.f ? -1.f : 1.f));
-            }
+            for (int r = 0; r < RL; ++r)
+                if (r < nv) {
+                    __stcs(o_lo + ch1 + static_cast<long long>(r) * P, lo[r] < 0.f ? -1.f : 1.f);
+                    __stcs(o_hi + ch1 + static_cast<long long>(r) * P, hi[r] < 0.f ? -1.f : 1.f);
+                }
         }
+        if (mode == 1) {
+#pragma unroll
+            for (int r = 0; r < RL; ++r) { lo[r] = ln_approx(fmaf(lo[r], lo[r], off)); hi[r] = ln_approx(fmaf(hi[r], hi[r], off)); }
+        } else if (mode == 2) {
+#pragma unroll
+            for (int r = 0; r < RL; ++r) { lo[r] = log_power(lo[r], ep.power, off, false); hi[r] = log_power(hi[r], ep.power, off, false); }
+        }
+#pragma unroll
+        for (int r = 0; r < RL; ++r)
+            if (r < nv) {
+                __stcs(o_lo + static_cast<long long>(r) * P, lo[r]);
+                __stcs(o_hi + static_cast<long long>(r) * P, hi[r]);
+            }
     }
 }
 
