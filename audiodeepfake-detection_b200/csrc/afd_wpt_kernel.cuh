@@ -62,6 +62,9 @@ struct Pass {
     int parent_base;   // natural index (within the half tree) of the first parent, last level only
     int prefetch;      // the next frame's first chunk may be staged while this pass runs
     int sync_before;   // barrier needed before this pass even if the previous pass ended with one
+    // chunk classification of the child nodes for the chosen item size (make_split, evaluated on the host)
+    int C, CL, CIe, CR, NI, NE;
+    unsigned magicNI;
 };
 
 struct WptPlan {
@@ -290,7 +293,8 @@ __device__ __forceinline__ void mid_level(const float* __restrict__ in, float* _
                                           const Coefs<F>& cf) {
     constexpr int padl = F - 2;
     const int n_out = ps.n_out;
-    const Split sp = make_split(n_out, R, padl);
+    Split sp;
+    sp.C = ps.C; sp.CL = ps.CL; sp.CIe = ps.CIe; sp.CR = ps.CR; sp.NI = ps.NI; sp.NE = ps.NE; sp.magicNI = ps.magicNI;
     const int parents = ps.parents;
     const int n_int = parents * sp.NI;
     const int total = parents * sp.C;
@@ -422,13 +426,29 @@ __device__ __forceinline__ void issue_chunk(const float* __restrict__ xg, float*
     const int r_lo = max(s_start, 0);
     const int r_hi = min(s_end, N);               // real samples [r_lo, r_hi)
     const int tid = threadIdx.x;
-    if ((reinterpret_cast<uintptr_t>(xg) & 7) == 0) {     // r_lo is even: 8-byte copies
-        const int pairs = (r_hi - r_lo) >> 1;
-        for (int i = tid; i < pairs; i += kThreads)
-            cp_async_8(buf + (r_lo - s_start) + 2 * i, xg + r_lo + 2 * i);
-        if (((r_hi - r_lo) & 1) && tid == 0) cp_async_4(buf + (r_hi - 1 - s_start), xg + r_hi - 1);
-    } else {
-        for (int i = r_lo + tid; i < r_hi; i += kThreads) cp_async_4(buf + (i - s_start), xg + i);
+    {
+        // widest copy both addresses allow (a frame is 88,200 B, so odd frames are only 8-byte aligned)
+        const char* src = reinterpret_cast<const char*>(xg + r_lo);
+        const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(buf + (r_lo - s_start)));
+        const int n = r_hi - r_lo;
+        const unsigned mis = static_cast<unsigned>(reinterpret_cast<uintptr_t>(src)) | dst;
+        if ((mis & 15) == 0) {
+            const int units = n >> 2;
+            const char* s = src + 16 * tid;
+            uint32_t d = dst + 16 * tid;
+            for (int i = tid; i < units; i += kThreads, s += 16 * kThreads, d += 16 * kThreads)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(s));
+            if (tid < (n & 3)) cp_async_4(buf + (r_lo - s_start) + 4 * units + tid, xg + r_lo + 4 * units + tid);
+        } else if ((mis & 7) == 0) {
+            const int units = n >> 1;
+            const char* s = src + 8 * tid;
+            uint32_t d = dst + 8 * tid;
+            for (int i = tid; i < units; i += kThreads, s += 8 * kThreads, d += 8 * kThreads)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(s));
+            if ((n & 1) && tid == 0) cp_async_4(buf + (r_hi - 1 - s_start), xg + r_hi - 1);
+        } else {
+            for (int i = r_lo + tid; i < r_hi; i += kThreads) cp_async_4(buf + (i - s_start), xg + i);
+        }
     }
     // reflect padding of the frame itself: x~[-i] = x[i], x~[N-1+i] = x[N-1-i]
     for (int s = s_start + tid; s < 0; s += kThreads) cp_async_4(buf + (s - s_start), xg - s);
@@ -597,6 +617,10 @@ static int make_plan(int64_t N, int F, int L, const Tuning& tu, int ctas_per_sm,
     auto pick = [&](int nodes, int n_out, int ra, int rb) {
         return level_cost(nodes, n_out, rb, tu.halo) < level_cost(nodes, n_out, ra, tu.halo) ? 1 : 0;
     };
+    auto fill_split = [&](Pass& ps, int R) {
+        const Split sp = make_split(ps.n_out, R, padl);
+        ps.C = sp.C; ps.CL = sp.CL; ps.CIe = sp.CIe; ps.CR = sp.CR; ps.NI = sp.NI; ps.NE = sp.NE; ps.magicNI = sp.magicNI;
+    };
     auto stored_mul = [&]() {                                 // factor for a stored level
         if (!tu.lat) return 1.0f;
         pending *= level_scale;
@@ -612,6 +636,7 @@ static int make_plan(int64_t N, int F, int L, const Tuning& tu, int ctas_per_sm,
         ps.in_stride = stride[l - 1]; ps.out_stride = stride[l];
         ps.rsel = pick(ps.parents, ps.n_out, tu.RA, tu.RB);
         ps.mul = stored_mul();
+        fill_split(ps, ps.rsel ? tu.RB : tu.RA);
     }
     const int nodes_lm1 = 1 << (L - 2);                       // level L-1 nodes of this half tree
     const int per_group = nodes_lm1 / G;
@@ -629,6 +654,7 @@ static int make_plan(int64_t N, int F, int L, const Tuning& tu, int ctas_per_sm,
             ps.in_stride = stride[L - 2]; ps.out_stride = stride[L - 1];
             ps.rsel = pick(par, ps.n_out, tu.RA, tu.RB);
             ps.mul = grouped_mul;
+            fill_split(ps, ps.rsel ? tu.RB : tu.RA);
             ps.sync_before = g > 0;                           // the level L-1 slice is being re-used
         }
         Pass& ps = p->pass[np++];
