@@ -758,7 +758,7 @@ static int dispatch_one(const float* x, int64_t B, int64_t N, int64_t x_row_stri
     lat.scale = 1.0;
     if constexpr (F <= 32) {
         if (lattice_factor(dec_lo, F, &lat) == AFD_OK && lat.usable)
-            return launch<F, pick_r1(F), 22, 30, 14, pick_rlb(F), true>(x, B, N, x_row_stride, out, L, dec_lo, lat, ep, stream, report);
+            return launch<F, pick_r1(F), 22, 26, 14, pick_rlb(F), true>(x, B, N, x_row_stride, out, L, dec_lo, lat, ep, stream, report);
         return launch<F, pick_r1(F), 14, 10, 14, 10, false>(x, B, N, x_row_stride, out, L, dec_lo, lat, ep, stream, report);
     } else {
         return launch<F, pick_r1(F), pick_rd(F), pick_rd(F), pick_rd(F), pick_rd(F), false>(
