@@ -394,8 +394,8 @@ __device__ __forceinline__ void last_level(const float* __restrict__ in, const P
 #pragma unroll
             for (int r = 0; r < RL; ++r)
                 if (r < nv) {
-                    __stcs(o_lo + ch1 + static_cast<long long>(r) * P, lo[r] < 0.f ? -1.f : 1.f);
-                    __stcs(o_hi + ch1 + static_cast<long long>(r) * P, hi[r] < 0.f ? -1.f : 1.f);
+                    __stcs(o_lo + ch1 + r * P, lo[r] < 0.f ? -1.f : 1.f);      // r * P < T * P < 2^31
+                    __stcs(o_hi + ch1 + r * P, hi[r] < 0.f ? -1.f : 1.f);
                 }
         }
         if (mode == 1) {
@@ -408,8 +408,8 @@ __device__ __forceinline__ void last_level(const float* __restrict__ in, const P
 #pragma unroll
         for (int r = 0; r < RL; ++r)
             if (r < nv) {
-                __stcs(o_lo + static_cast<long long>(r) * P, lo[r]);
-                __stcs(o_hi + static_cast<long long>(r) * P, hi[r]);
+                __stcs(o_lo + r * P, lo[r]);
+                __stcs(o_hi + r * P, hi[r]);
             }
     }
 }
