@@ -3,18 +3,46 @@
 // caller of the reference (numpy in / numpy out, e.g. scripts/freq_visual/fingerprints.py) would use.
 #include <algorithm>
 #include <functional>
+#include <map>
+#include <mutex>
 
 #include "afd_common.cuh"
 
 namespace afd {
 
-constexpr int kSlots = 3;
+constexpr int kSlots = 4;
 
-struct Slot {
-    cudaStream_t stream = nullptr;
-    float* d_in = nullptr;
-    float* d_out = nullptr;
+// Per-device pipeline state, created on first use and kept for the life of the process: streams and device
+// staging buffers are reused by every host-buffer call (cudaMalloc / cudaFree per call would serialise the
+// device and cost more than the copies of a small batch).  One host call at a time per device.
+struct Pipeline {
+    std::mutex mu;
+    cudaStream_t stream[kSlots] = {};
+    float* d_in[kSlots] = {};
+    float* d_out[kSlots] = {};
+    size_t in_cap[kSlots] = {};
+    size_t out_cap[kSlots] = {};
 };
+
+static std::mutex g_pipe_mutex;
+static std::map<int, Pipeline*> g_pipes;
+
+static Pipeline* pipeline_for(int device) {
+    std::lock_guard<std::mutex> lock(g_pipe_mutex);
+    auto it = g_pipes.find(device);
+    if (it != g_pipes.end()) return it->second;
+    Pipeline* p = new Pipeline();
+    g_pipes[device] = p;
+    return p;
+}
+
+static cudaError_t ensure(float** buf, size_t* cap, size_t bytes) {
+    if (*cap >= bytes) return cudaSuccess;
+    if (*buf) { cudaFree(*buf); *buf = nullptr; *cap = 0; }
+    cudaError_t e = cudaMalloc(buf, bytes);
+    if (e == cudaSuccess) *cap = bytes;
+    return e;
+}
 
 // launch(d_in, d_out, nb, stream) must enqueue the device transform of nb frames.
 static int run_pipelined(const float* x_host, int64_t B, int64_t N, int64_t x_row_stride, float* out_host,
@@ -25,46 +53,45 @@ static int run_pipelined(const float* x_host, int64_t B, int64_t N, int64_t x_ro
     AFD_CUDA_TRY(cudaSetDevice(device));
     if (chunk <= 0) chunk = 512;
     chunk = std::min<int64_t>(chunk, std::max<int64_t>(B, 1));
-    Slot slots[kSlots];
+    Pipeline* pl = pipeline_for(device);
+    std::lock_guard<std::mutex> lock(pl->mu);
     int rc = AFD_OK;
-    auto cleanup = [&]() {
-        for (auto& s : slots) {
-            if (s.d_in) cudaFree(s.d_in);
-            if (s.d_out) cudaFree(s.d_out);
-            if (s.stream) cudaStreamDestroy(s.stream);
-        }
-        cudaSetDevice(prev);
-    };
     const int nslots = static_cast<int>(std::min<int64_t>(kSlots, (B + chunk - 1) / chunk));
     for (int i = 0; i < nslots && rc == AFD_OK; ++i) {
-        cudaError_t e = cudaStreamCreateWithFlags(&slots[i].stream, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaMalloc(&slots[i].d_in, sizeof(float) * chunk * N);
-        if (e == cudaSuccess && out_row_floats > 0) e = cudaMalloc(&slots[i].d_out, sizeof(float) * chunk * out_row_floats);
+        cudaError_t e = cudaSuccess;
+        if (!pl->stream[i]) e = cudaStreamCreateWithFlags(&pl->stream[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = ensure(&pl->d_in[i], &pl->in_cap[i], sizeof(float) * chunk * N);
+        if (e == cudaSuccess && out_row_floats > 0)
+            e = ensure(&pl->d_out[i], &pl->out_cap[i], sizeof(float) * chunk * out_row_floats);
         if (e != cudaSuccess) rc = cuda_fail(e, "pipeline slot allocation");
     }
     int64_t done = 0;
     for (int64_t c = 0; rc == AFD_OK && done < B; ++c) {
-        Slot& s = slots[c % nslots];
+        const int i = static_cast<int>(c % nslots);
+        cudaStream_t s = pl->stream[i];
         const int64_t nb = std::min(chunk, B - done);
-        cudaError_t e = cudaMemcpy2DAsync(s.d_in, sizeof(float) * N, x_host + done * x_row_stride,
-                                          sizeof(float) * x_row_stride, sizeof(float) * N, nb,
-                                          cudaMemcpyHostToDevice, s.stream);
+        cudaError_t e;
+        if (x_row_stride == N)
+            e = cudaMemcpyAsync(pl->d_in[i], x_host + done * N, sizeof(float) * nb * N, cudaMemcpyHostToDevice, s);
+        else
+            e = cudaMemcpy2DAsync(pl->d_in[i], sizeof(float) * N, x_host + done * x_row_stride,
+                                  sizeof(float) * x_row_stride, sizeof(float) * N, nb, cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) { rc = cuda_fail(e, "H2D copy"); break; }
-        rc = launch(s.d_in, s.d_out, nb, s.stream);
+        rc = launch(pl->d_in[i], pl->d_out[i], nb, s);
         if (rc != AFD_OK) break;
         if (out_row_floats > 0) {
-            e = cudaMemcpyAsync(out_host + done * out_row_floats, s.d_out, sizeof(float) * nb * out_row_floats,
-                                cudaMemcpyDeviceToHost, s.stream);
+            e = cudaMemcpyAsync(out_host + done * out_row_floats, pl->d_out[i], sizeof(float) * nb * out_row_floats,
+                                cudaMemcpyDeviceToHost, s);
             if (e != cudaSuccess) { rc = cuda_fail(e, "D2H copy"); break; }
         }
         done += nb;
     }
     for (int i = 0; i < nslots; ++i) {
-        if (!slots[i].stream) continue;
-        cudaError_t e = cudaStreamSynchronize(slots[i].stream);
+        if (!pl->stream[i]) continue;
+        cudaError_t e = cudaStreamSynchronize(pl->stream[i]);
         if (e != cudaSuccess && rc == AFD_OK) rc = cuda_fail(e, "pipeline synchronize");
     }
-    cleanup();
+    cudaSetDevice(prev);
     return rc;
 }
 
@@ -122,7 +149,9 @@ extern "C" int afd_haar_fingerprint_host(const float* x_host, int64_t B, int64_t
     cudaError_t e = cudaMalloc(&d_sums, P * sizeof(double) + sizeof(long long));
     if (e != cudaSuccess) { cudaSetDevice(prev); return cuda_fail(e, "cudaMalloc(sums)"); }
     d_count = reinterpret_cast<long long*>(d_sums + P);
-    cudaMemset(d_sums, 0, P * sizeof(double) + sizeof(long long));
+    e = cudaMemset(d_sums, 0, P * sizeof(double) + sizeof(long long));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);   // the pipeline streams are non-blocking: they would not wait for it
+    if (e != cudaSuccess) { cudaFree(d_sums); cudaSetDevice(prev); return cuda_fail(e, "cudaMemset(sums)"); }
     // every chunk accumulates into the same device sums: atomics make the slots' kernels commute
     int rc = B == 0 ? AFD_OK
                     : run_pipelined(x_host, B, N, x_row_stride, nullptr, 0, device, chunk_frames,

@@ -18,6 +18,8 @@
 // tile, and the lanes run the second 32-point FFT.  The spectrum of the chirp (with the 1/M of the inverse
 // transform folded in) is computed on the host in double precision once per (n_fft) and cached per device.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <map>
 #include <mutex>
@@ -283,6 +285,11 @@ static int get_tables(int dev, int n, float2** out) {
     return AFD_OK;
 }
 
+// afd_stft_pfa.cu: prime-factor / tensor-core path for n_fft = 511
+bool stft_pfa511_supported(const float* x, int64_t N, int n_fft, int hop, const float* out);
+int stft_pfa511_launch(const float* x, int64_t B, int64_t N, int64_t x_row_stride, int hop, float power, int log_scale,
+                       float log_offset, float* out, cudaStream_t stream);
+
 }  // namespace afd
 
 using namespace afd;
@@ -305,6 +312,15 @@ extern "C" int afd_stft_power(const float* x, int64_t B, int64_t N, int64_t x_ro
         return fail(AFD_ERR_REFLECT_PAD, "afd_stft_power: reflect padding %d must be smaller than the signal length %lld", n_fft / 2, (long long)N);
     if (N > (1LL << 30)) return fail(AFD_ERR_UNSUPPORTED, "afd_stft_power: signal too long");
     if (B == 0) return AFD_OK;
+    {
+        // n_fft = 511 (the reference's 2*num_of_scales-1) takes the prime-factor tensor-core kernel; AFD_STFT_IMPL=bluestein
+        // forces the generic chirp-z kernel (used by the parity tests to cover both).
+        const char* impl = getenv("AFD_STFT_IMPL");
+        const bool force_generic = impl && strcmp(impl, "bluestein") == 0;
+        if (!force_generic && stft_pfa511_supported(x, N, n_fft, hop, out))
+            return stft_pfa511_launch(x, B, N, x_row_stride, hop, power, log_scale, log_offset, out,
+                                      static_cast<cudaStream_t>(stream));
+    }
     int dev = 0;
     AFD_CUDA_TRY(cudaGetDevice(&dev));
     float2* tables = nullptr;

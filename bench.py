@@ -236,6 +236,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline leg")
+    ap.add_argument("--e2e-chunk", type=int, default=512, help="frames per pipelined chunk of the host-buffer call")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -329,7 +330,7 @@ def main():
             def host_step():
                 _lib.check("afd_wpt_forward_host", lib.afd_wpt_forward_host(
                     ctypes.c_void_p(xh.data_ptr()), B, N_SAMPLES, N_SAMPLES, taps, len(wav.dec_lo), level, 0, 2.0, 1,
-                    1e-12, 0, ctypes.c_void_p(oh.data_ptr()), None, local_rank, 512))
+                    1e-12, 0, ctypes.c_void_p(oh.data_ptr()), None, local_rank, args.e2e_chunk))
             d2h = oh.numel() * 4
         elif kind == "stft":
             frames, bins = afd.stft_out_shape(N_SAMPLES, 511, 220)
@@ -338,7 +339,7 @@ def main():
             def host_step():
                 _lib.check("afd_stft_power_host", lib.afd_stft_power_host(
                     ctypes.c_void_p(xh.data_ptr()), B, N_SAMPLES, N_SAMPLES, 511, 220, 2.0, 1, 1e-12,
-                    ctypes.c_void_p(oh.data_ptr()), local_rank, 512))
+                    ctypes.c_void_p(oh.data_ptr()), local_rank, args.e2e_chunk))
             d2h = oh.numel() * 4
         else:
             sums = torch.zeros(1 << level, dtype=torch.float64)
@@ -347,7 +348,7 @@ def main():
             def host_step():
                 _lib.check("afd_haar_fingerprint_host", lib.afd_haar_fingerprint_host(
                     ctypes.c_void_p(xh.data_ptr()), B, N_SAMPLES, N_SAMPLES, level, ctypes.c_void_p(sums.data_ptr()),
-                    ctypes.byref(cnt), local_rank, 512))
+                    ctypes.byref(cnt), local_rank, args.e2e_chunk))
             d2h = sums.numel() * 8 + 8
         for _ in range(2):
             host_step()
@@ -362,8 +363,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": B * world * e2e_steps / float(t.item()), "unit": "frames/s",
                "h2d_bytes_per_step": B * N_SAMPLES * 4, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-               "api": "afd_%s_host (C ABI, pinned host buffers, 512-frame chunks on 3 streams)" %
-                      {"packets": "wpt_forward", "stft": "stft_power", "haar": "haar_fingerprint"}[kind]}
+               "api": "afd_%s_host (C ABI, pinned host buffers, %d-frame chunks on 4 streams)" %
+                      ({"packets": "wpt_forward", "stft": "stft_power", "haar": "haar_fingerprint"}[kind], args.e2e_chunk)}
 
     if rank != 0:
         if world > 1:

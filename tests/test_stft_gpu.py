@@ -87,3 +87,50 @@ def test_parseval_full_batch(cuda_device):
     total = 2 * spec[:, 0].double().sum(-1) - dc                        # odd n: every bin but DC appears twice
     assert float(((total - energy).abs() / energy).max()) < 1e-4
     assert torch.equal(spec, afd.stft_power_features(x))               # bitwise reproducible
+
+
+@pytest.mark.parametrize("hop,N,B", [(220, 22050, 37), (100, 8000, 3), (242, 22050, 2), (1, 700, 2), (243, 22050, 2),
+                                     (220, 256, 3), (220, 3000, 17)])
+def test_pfa511_tensor_core_path(hop, N, B, cuda_device, monkeypatch):
+    """n_fft = 511 takes the prime-factor / tensor-core kernel (hop <= 242): fp64 DFT parity, and agreement with the
+    generic chirp-z kernel forced through AFD_STFT_IMPL=bluestein (hop 243 is served by the generic kernel anyway)."""
+    rng = np.random.default_rng(hop * 7 + N)
+    x = (rng.standard_normal((B, N)) * 0.1).astype(np.float32)
+    want = ptwt_like.stft_power_explicit(torch.from_numpy(x).double().unsqueeze(1), 511, hop).numpy()
+    xt = torch.from_numpy(x).to(cuda_device)
+    monkeypatch.delenv("AFD_STFT_IMPL", raising=False)
+    got = afd.stft_power_features(xt, 511, hop).cpu().numpy()
+    assert got.shape == want[:, :, :, :].transpose(0, 1, 3, 2).shape
+    assert _rel(got, want.transpose(0, 1, 3, 2)) < TOL
+    monkeypatch.setenv("AFD_STFT_IMPL", "bluestein")
+    other = afd.stft_power_features(xt, 511, hop).cpu().numpy()
+    assert _rel(got, other) < TOL
+
+
+def test_pfa511_misaligned_rows(cuda_device, monkeypatch):
+    """Rows that start at every 4-byte phase (views into a larger buffer): the staging copy falls back from 16-byte to
+    element-wise cp.async and the result must not change."""
+    monkeypatch.delenv("AFD_STFT_IMPL", raising=False)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    big = torch.randn(6, 22050 + 7, device=cuda_device, generator=g) * 0.1
+    base = afd.stft_power_features(big[:, :22050].contiguous())
+    for off in (0, 1, 2, 3, 5):
+        view = big[:, off:off + 22050]
+        ref = afd.stft_power_features(view.contiguous())
+        got = afd.stft_power_features(view)          # row stride 22057, base pointer off*4 bytes past 16-byte alignment
+        assert torch.equal(got, ref)
+    assert torch.isfinite(base).all()
+
+
+def test_pfa511_log_and_power(cuda_device, monkeypatch):
+    monkeypatch.delenv("AFD_STFT_IMPL", raising=False)
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((3, 22050)) * 0.1).astype(np.float32)
+    truth = ptwt_like.stft_power_dft64(x).transpose(0, 2, 1)                # [B, frames, bins] fp64
+    xt = torch.from_numpy(x).to(cuda_device)
+    logs = afd.stft_power_features(xt, 511, 220, 2.0, True)[:, 0].cpu().numpy()
+    want = np.log(truth + 1e-12)
+    big = truth > 1e-6 * truth.max()
+    assert np.max(np.abs(logs - want)[big]) < LOG_TOL * np.max(np.abs(want))
+    mag = afd.stft_power_features(xt, 511, 220, 1.0, False)[:, 0].cpu().numpy()
+    assert _rel(mag, np.sqrt(truth)) < 1e-4
