@@ -10,6 +10,10 @@ from .wavelet_math import (  # noqa: F401
     Normalize,
     compute_pytorch_packet_representation,
     get_transforms,
+    calc_normalization,
+    fuse_normalize,
+    NodeStats,
+    NodeStatsTable,
     normalization_stats,
     stft_power_features,
     wavelet_packet_features,

@@ -21,10 +21,15 @@ SIGNATURES = {
     "afd_wpt_out_len": (c_int, [c_int64, c_int, c_int, POINTER(c_int64)]),
     "afd_wpt_forward": (c_int, [c_void_p, c_int64, c_int64, c_int64, POINTER(c_double), c_int, c_int, c_int,
                                 c_float, c_int, c_float, c_int, c_void_p, POINTER(c_int64), c_void_p]),
+    "afd_wpt_forward_ex": (c_int, [c_void_p, c_int64, c_int64, c_int64, POINTER(c_double), c_int, c_int, c_int,
+                                   c_float, c_int, c_float, c_int, c_void_p, POINTER(c_float), c_void_p, c_void_p,
+                                   c_void_p, POINTER(c_int64), c_void_p]),
     "afd_wpt_forward_host": (c_int, [c_void_p, c_int64, c_int64, c_int64, POINTER(c_double), c_int, c_int, c_int,
                                      c_float, c_int, c_float, c_int, c_void_p, POINTER(c_int64), c_int, c_int64]),
     "afd_stft_power": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_float, c_int, c_float,
                                c_void_p, c_void_p]),
+    "afd_stft_power_ex": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_float, c_int, c_float,
+                                  POINTER(c_float), c_void_p, c_void_p, c_void_p]),
     "afd_stft_out_shape": (c_int, [c_int64, c_int, c_int, POINTER(c_int64), POINTER(c_int64)]),
     "afd_stft_power_host": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_float, c_int, c_float,
                                     c_void_p, c_int, c_int64]),

@@ -25,6 +25,13 @@ struct LatticeInfo {
 };
 int lattice_factor(const double* dec_lo, int F, LatticeInfo* info);
 
+// Extended STFT epilogue (afd_stft_power_ex): fused Normalize and feature moments.
+struct StftExtras {
+    int normalize;
+    float nmean, nrstd;
+    double* moments;
+};
+
 void set_error(const char* fmt, ...);
 int fail(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);

@@ -121,12 +121,16 @@ struct StftParams {
     long long total_pairs;  // B * pairs_per_row
     float power, log_offset;
     int log_scale, square;
+    int normalize, store;   // extended epilogue (afd_stft_power_ex)
+    float nmean, nrstd;
+    double* moments;
 };
 
 // Tables (device, per n_fft): [0,n)      a_tab[j] = hann[j] * conj(c[j])        (float2)
 //                             [n,2n)     post[k]  = conj(c[k])                  (float2)
 //                             [2n,2n+M)  bspec[q] = FFT_M(chirp)[q] / M         (float2)
 //                             [2n+M, +M) tw2d[kr*32+l] = exp(-2 pi i l kr / M)  (float2)
+template <bool EXT>
 __global__ void __launch_bounds__(kStftWarps * 32, 2)
 stft_bluestein_kernel(const float* __restrict__ x, long long x_row_stride, float* __restrict__ out,
                       const float2* __restrict__ tables, const __grid_constant__ StftParams p) {
@@ -148,6 +152,7 @@ stft_bluestein_kernel(const float* __restrict__ x, long long x_row_stride, float
     float2* tile = s_tiles + warp * kTileFloat2;
     const long long warps_total = static_cast<long long>(gridDim.x) * kStftWarps;
     const bool square = p.square != 0;
+    float mom_s = 0.f, mom_q = 0.f;
 
     for (long long pr = static_cast<long long>(blockIdx.x) * kStftWarps + warp; pr < p.total_pairs; pr += warps_total) {
         const long long b = pr / p.pairs_per_row;
@@ -212,10 +217,31 @@ stft_bluestein_kernel(const float* __restrict__ x, long long x_row_stride, float
                 p1 = __logf(p1 + p.log_offset);
                 p2 = __logf(p2 + p.log_offset);
             }
-            st_cs(o1 + k, p1);
-            if (has2) st_cs(o1 + p.bins + k, p2);
+            if (EXT && p.moments) {
+                mom_s += p1; mom_q = fmaf(p1, p1, mom_q);
+                if (has2) { mom_s += p2; mom_q = fmaf(p2, p2, mom_q); }
+            }
+            if (EXT && p.normalize) {
+                p1 = (p1 - p.nmean) * p.nrstd;
+                p2 = (p2 - p.nmean) * p.nrstd;
+            }
+            if (!EXT || p.store) {
+                st_cs(o1 + k, p1);
+                if (has2) st_cs(o1 + p.bins + k, p2);
+            }
         }
         __syncwarp();
+    }
+    if (EXT && p.moments) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mom_s += __shfl_xor_sync(0xffffffffu, mom_s, o);
+            mom_q += __shfl_xor_sync(0xffffffffu, mom_q, o);
+        }
+        if (lane == 0) {
+            atomicAdd(p.moments, static_cast<double>(mom_s));
+            atomicAdd(p.moments + 1, static_cast<double>(mom_q));
+        }
     }
 }
 
@@ -288,7 +314,7 @@ static int get_tables(int dev, int n, float2** out) {
 // afd_stft_pfa.cu: prime-factor / tensor-core path for n_fft = 511
 bool stft_pfa511_supported(const float* x, int64_t N, int n_fft, int hop, const float* out);
 int stft_pfa511_launch(const float* x, int64_t B, int64_t N, int64_t x_row_stride, int hop, float power, int log_scale,
-                       float log_offset, float* out, cudaStream_t stream);
+                       float log_offset, const StftExtras& ex, float* out, cudaStream_t stream);
 
 }  // namespace afd
 
@@ -301,9 +327,9 @@ extern "C" int afd_stft_out_shape(int64_t N, int n_fft, int hop, int64_t* frames
     return AFD_OK;
 }
 
-extern "C" int afd_stft_power(const float* x, int64_t B, int64_t N, int64_t x_row_stride, int n_fft, int hop,
-                              float power, int log_scale, float log_offset, float* out, void* stream) {
-    if ((!x || !out) && B != 0) return fail(AFD_ERR_INVALID_ARG, "afd_stft_power: null pointer");
+static int stft_power_impl(const float* x, int64_t B, int64_t N, int64_t x_row_stride, int n_fft, int hop,
+                           float power, int log_scale, float log_offset, const StftExtras& ex, float* out, void* stream) {
+    if ((!x || (!out && !ex.moments)) && B != 0) return fail(AFD_ERR_INVALID_ARG, "afd_stft_power: null pointer");
     if (B < 0 || N < 2 || x_row_stride < N || hop < 1) return fail(AFD_ERR_INVALID_ARG, "afd_stft_power: bad B/N/stride/hop");
     if (n_fft < 2) return fail(AFD_ERR_INVALID_ARG, "afd_stft_power: n_fft must be >= 2");
     if (2 * n_fft - 1 > kFftM)
@@ -318,7 +344,7 @@ extern "C" int afd_stft_power(const float* x, int64_t B, int64_t N, int64_t x_ro
         const char* impl = getenv("AFD_STFT_IMPL");
         const bool force_generic = impl && strcmp(impl, "bluestein") == 0;
         if (!force_generic && stft_pfa511_supported(x, N, n_fft, hop, out))
-            return stft_pfa511_launch(x, B, N, x_row_stride, hop, power, log_scale, log_offset, out,
+            return stft_pfa511_launch(x, B, N, x_row_stride, hop, power, log_scale, log_offset, ex, out,
                                       static_cast<cudaStream_t>(stream));
     }
     int dev = 0;
@@ -333,19 +359,42 @@ extern "C" int afd_stft_power(const float* x, int64_t B, int64_t N, int64_t x_ro
     p.pairs_per_row = (p.frames + 1) / 2;
     p.total_pairs = B * static_cast<long long>(p.pairs_per_row);
     p.power = power; p.log_offset = log_offset; p.log_scale = log_scale ? 1 : 0; p.square = (power == 2.0f);
+    p.normalize = ex.normalize; p.nmean = ex.nmean; p.nrstd = ex.nrstd; p.moments = ex.moments; p.store = out != nullptr;
     const int smem = static_cast<int>(sizeof(float2)) * (2 * kFftM + kStftWarps * kTileFloat2);
-    static thread_local bool configured[16] = {false};
-    if (dev >= 16 || !configured[dev]) {
-        AFD_CUDA_TRY(cudaFuncSetAttribute(stft_bluestein_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        if (dev < 16) configured[dev] = true;
+    const bool ext = ex.normalize || ex.moments || !out;
+    auto kern = ext ? stft_bluestein_kernel<true> : stft_bluestein_kernel<false>;
+    static thread_local bool configured[2][16] = {{false}, {false}};
+    if (dev >= 16 || !configured[ext][dev]) {
+        AFD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (dev < 16) configured[ext][dev] = true;
     }
     int sms = kNumSmsFallback;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long blocks = (p.total_pairs + kStftWarps - 1) / kStftWarps;
     const long long max_blocks = 2LL * sms;   // persistent: 2 CTAs (16 warps) per SM, register-bound
     if (blocks > max_blocks) blocks = max_blocks;
-    stft_bluestein_kernel<<<static_cast<unsigned>(blocks), kStftWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+    kern<<<static_cast<unsigned>(blocks), kStftWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
         x, static_cast<long long>(x_row_stride), out, tables, p);
     AFD_CUDA_TRY(cudaGetLastError());
     return AFD_OK;
+}
+
+extern "C" int afd_stft_power(const float* x, int64_t B, int64_t N, int64_t x_row_stride, int n_fft, int hop,
+                              float power, int log_scale, float log_offset, float* out, void* stream) {
+    if (!out && B != 0) return fail(AFD_ERR_INVALID_ARG, "afd_stft_power: null pointer");
+    return stft_power_impl(x, B, N, x_row_stride, n_fft, hop, power, log_scale, log_offset, StftExtras{}, out, stream);
+}
+
+extern "C" int afd_stft_power_ex(const float* x, int64_t B, int64_t N, int64_t x_row_stride, int n_fft, int hop,
+                                 float power, int log_scale, float log_offset, const float* norm_mean_std_host,
+                                 double* feat_moments, float* out, void* stream) {
+    StftExtras ex{};
+    ex.moments = feat_moments;
+    if (norm_mean_std_host) {
+        const float mean = norm_mean_std_host[0], std = norm_mean_std_host[1];
+        if (!(std > 0.f) || !isfinite(mean) || !isfinite(std))
+            return fail(AFD_ERR_INVALID_ARG, "afd_stft_power_ex: needs a finite mean and a positive std");
+        ex.normalize = 1; ex.nmean = mean; ex.nrstd = 1.0f / std;
+    }
+    return stft_power_impl(x, B, N, x_row_stride, n_fft, hop, power, log_scale, log_offset, ex, out, stream);
 }

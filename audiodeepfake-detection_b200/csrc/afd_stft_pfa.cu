@@ -58,6 +58,10 @@ struct PfaParams {
     long long total_units;
     float power, log_offset;
     int log_scale, square;
+    // extended epilogue (afd_stft_power_ex)
+    int normalize, store;
+    float nmean, nrstd;
+    double* moments;           // device [2]: sum / sum of squares of the features before normalisation
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -166,6 +170,7 @@ __device__ __forceinline__ float pfa_finish(float re, float im, const PfaParams&
 }
 
 // tables (device, float): [0, kPfaBFloats) B fragments; then kPfaWFloats window values.
+template <bool EXT>
 __global__ void __launch_bounds__(kPfaThreads, 1)
 stft_pfa511_kernel(const float* __restrict__ x, long long x_row_stride, float* __restrict__ out,
                    const float* __restrict__ tables, const __grid_constant__ PfaParams p) {
@@ -224,6 +229,8 @@ stft_pfa511_kernel(const float* __restrict__ x, long long x_row_stride, float* _
     const uint32_t a_addr = smem_u32(s_a) + ((s_first * kPfaRows + lrow) * kPfaAStride + lcol) * 4;
     const float4* const btab = reinterpret_cast<const float4*>(s_b);
 
+    float mom_s = 0.f, mom_q = 0.f;
+    const float n_rs = (EXT && p.normalize) ? p.nrstd : 1.f, n_dm = (EXT && p.normalize) ? -p.nmean * p.nrstd : 0.f;
     const long long gstride = static_cast<long long>(gridDim.x) * kPfaGroups;
     long long unit = static_cast<long long>(blockIdx.x) * kPfaGroups + grp;
     if (unit < p.total_units) {
@@ -317,12 +324,31 @@ stft_pfa511_kernel(const float* __restrict__ x, long long x_row_stride, float* _
             float* og = out + (b * p.frames + t0) * 256LL;
             for (int i = gt; i < valid * 64; i += kPfaGroupThreads) {
                 const int row = i >> 6, c4 = (i & 63) * 4;
-                const float4 v = *reinterpret_cast<const float4*>(s_out + row * kPfaOutStride + c4);
-                st_cs4(reinterpret_cast<float4*>(og + row * 256 + c4), v);
+                float4 v = *reinterpret_cast<const float4*>(s_out + row * kPfaOutStride + c4);
+                if (EXT && p.moments) {
+                    mom_s += (v.x + v.y) + (v.z + v.w);
+                    mom_q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, mom_q))));
+                }
+                if (EXT && p.normalize) {
+                    v.x = fmaf(v.x, n_rs, n_dm); v.y = fmaf(v.y, n_rs, n_dm);
+                    v.z = fmaf(v.z, n_rs, n_dm); v.w = fmaf(v.w, n_rs, n_dm);
+                }
+                if (!EXT || p.store) st_cs4(reinterpret_cast<float4*>(og + row * 256 + c4), v);
             }
         }
     }
     cp_async_wait<0>();
+    if (EXT && p.moments) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mom_s += __shfl_xor_sync(0xffffffffu, mom_s, o);
+            mom_q += __shfl_xor_sync(0xffffffffu, mom_q, o);
+        }
+        if (lane == 0) {
+            atomicAdd(p.moments, static_cast<double>(mom_s));
+            atomicAdd(p.moments + 1, static_cast<double>(mom_q));
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -385,7 +411,7 @@ bool stft_pfa511_supported(const float* x, int64_t N, int n_fft, int hop, const 
 }
 
 int stft_pfa511_launch(const float* x, int64_t B, int64_t N, int64_t x_row_stride, int hop, float power, int log_scale,
-                       float log_offset, float* out, cudaStream_t stream) {
+                       float log_offset, const StftExtras& ex, float* out, cudaStream_t stream) {
     int dev = 0;
     AFD_CUDA_TRY(cudaGetDevice(&dev));
     float* tables = nullptr;
@@ -398,19 +424,21 @@ int stft_pfa511_launch(const float* x, int64_t B, int64_t N, int64_t x_row_strid
     p.total_units = B * static_cast<long long>(p.units_per_row);
     p.vec_ok = (reinterpret_cast<uintptr_t>(x) & 15) == 0 ? 1 : 0;
     p.power = power; p.log_offset = log_offset; p.log_scale = log_scale ? 1 : 0; p.square = (power == 2.0f);
+    p.normalize = ex.normalize; p.nmean = ex.nmean; p.nrstd = ex.nrstd; p.moments = ex.moments; p.store = out != nullptr;
     const int smem = static_cast<int>(sizeof(float)) *
                      (kPfaBFloats + kPfaWFloats + kPfaGroups * (kPfaAFloats + kPfaRawFloats));
-    static thread_local bool configured[16] = {false};
-    if (dev >= 16 || !configured[dev]) {
-        AFD_CUDA_TRY(cudaFuncSetAttribute(stft_pfa511_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        if (dev < 16) configured[dev] = true;
+    const bool ext = ex.normalize || ex.moments || !out;
+    auto kern = ext ? stft_pfa511_kernel<true> : stft_pfa511_kernel<false>;
+    static thread_local bool configured[2][16] = {{false}, {false}};
+    if (dev >= 16 || !configured[ext][dev]) {
+        AFD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (dev < 16) configured[ext][dev] = true;
     }
     int sms = kNumSmsFallback;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long blocks = (p.total_units + kPfaGroups - 1) / kPfaGroups;
     if (blocks > sms) blocks = sms;
-    stft_pfa511_kernel<<<static_cast<unsigned>(blocks), kPfaThreads, smem, stream>>>(
-        x, static_cast<long long>(x_row_stride), out, tables, p);
+    kern<<<static_cast<unsigned>(blocks), kPfaThreads, smem, stream>>>(x, static_cast<long long>(x_row_stride), out, tables, p);
     AFD_CUDA_TRY(cudaGetLastError());
     return AFD_OK;
 }

@@ -2,5 +2,5 @@
 #include "afd_wpt_kernel.cuh"
 
 namespace afd {
-AFD_WPT_GROUP(wpt_group0, 2)
+AFD_WPT_GROUP(wpt_group0, 2, false)
 }  // namespace afd

@@ -2,5 +2,5 @@
 #include "afd_wpt_kernel.cuh"
 
 namespace afd {
-AFD_WPT_GROUP(wpt_group1, 18)
+AFD_WPT_GROUP(wpt_group1, 18, false)
 }  // namespace afd

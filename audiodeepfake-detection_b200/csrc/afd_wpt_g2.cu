@@ -2,5 +2,5 @@
 #include "afd_wpt_kernel.cuh"
 
 namespace afd {
-AFD_WPT_GROUP(wpt_group2, 34)
+AFD_WPT_GROUP(wpt_group2, 34, false)
 }  // namespace afd

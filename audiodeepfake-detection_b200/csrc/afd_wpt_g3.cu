@@ -2,5 +2,5 @@
 #include "afd_wpt_kernel.cuh"
 
 namespace afd {
-AFD_WPT_GROUP(wpt_group3, 50)
+AFD_WPT_GROUP(wpt_group3, 50, false)
 }  // namespace afd

@@ -89,7 +89,58 @@ struct Epilogue {
     int sign_channel;
     int order;
     int square;  // power == 2
+    // ---- extended epilogue (afd_wpt_forward_ex); all off / null for afd_wpt_forward
+    const float* node_scale;   // device [P]: coefficient of output column p is multiplied by node_scale[p] (block norm)
+    double* node_stats;        // device [3][P]: sum c, sum c^2, max |c| of the raw coefficients per output column
+    double* feat_moments;      // device [C][2]: sum / sum of squares of the features written to each channel
+    int normalize;             // features leave as (v - nmean[c]) * nrstd[c]
+    float nmean[2];
+    float nrstd[2];
+    int stats_simple;          // every thread keeps one column pair for the whole launch: statistics stay in registers
+    int store;                 // 0: statistics only, nothing is written to `out`
 };
+
+// Per-thread running statistics (registers for the whole persistent loop when Epilogue::stats_simple).
+struct ThreadStats {
+    float s[2], q[2], m[2];    // sum, sum of squares, max |c| of the thread's (lo, hi) columns
+    int col[2];                // output columns they belong to (-1: nothing accumulated)
+    float fs[2], fq[2];        // feature sum / sum of squares per channel
+};
+
+__device__ __forceinline__ void atomic_max_nonneg(double* p, double v) {
+    // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(__double_as_longlong(v)));
+}
+
+__device__ __forceinline__ void flush_node_stats(const Epilogue& ep, int P, ThreadStats& ts) {
+    if (ts.col[0] < 0) return;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        atomicAdd(ep.node_stats + ts.col[i], static_cast<double>(ts.s[i]));
+        atomicAdd(ep.node_stats + P + ts.col[i], static_cast<double>(ts.q[i]));
+        atomic_max_nonneg(ep.node_stats + 2 * P + ts.col[i], static_cast<double>(ts.m[i]));
+        ts.s[i] = 0.f; ts.q[i] = 0.f; ts.m[i] = 0.f;
+    }
+    ts.col[0] = -1;
+}
+
+__device__ __forceinline__ void flush_feat_moments(const Epilogue& ep, int C, ThreadStats& ts) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        if (c >= C) break;
+        float a = ts.fs[c], b = ts.fq[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(ep.feat_moments + 2 * c, static_cast<double>(a));
+            atomicAdd(ep.feat_moments + 2 * c + 1, static_cast<double>(b));
+        }
+        ts.fs[c] = 0.f; ts.fq[c] = 0.f;
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // Direct form: R outputs (of one or both filters) from a register window.  w[j] = x~[2*k0 + 2 - F + j];
@@ -361,9 +412,10 @@ __device__ __forceinline__ unsigned igray(unsigned x) {
 }
 
 // Last level: `parents` padded nodes (level L-1) -> features in global memory.  Lanes map to parents.
-template <int F, int RL, bool LAT>
+template <int F, int RL, bool LAT, bool EXT>
 __device__ __forceinline__ void last_level(const float* __restrict__ in, const Pass& ps, int T, int half_base,
-                                           float* __restrict__ out_b, int P, const Coefs<F>& cf, const Epilogue& ep) {
+                                           float* __restrict__ out_b, int P, const Coefs<F>& cf, const Epilogue& ep,
+                                           ThreadStats& ts) {
     const int parents = ps.parents;
     const int chunks = (T + RL - 1) / RL;
     const int total = parents * chunks;
@@ -372,6 +424,7 @@ __device__ __forceinline__ void last_level(const float* __restrict__ in, const P
     const int mode = !ep.log_scale ? 0 : (ep.square ? 1 : 2);    // 0 raw, 1 log(c^2 + off), 2 log(|c|^p + off)
     const float off = ep.log_offset;
     const long long ch1 = static_cast<long long>(T) * P;
+    constexpr bool extended = EXT;                                   // afd_wpt_forward_ex instantiation
     for (int it = threadIdx.x; it < total; it += kThreads) {
         const int m = it & (parents - 1);
         const int c = it >> ps.lg_parents;
@@ -387,15 +440,42 @@ __device__ __forceinline__ void last_level(const float* __restrict__ in, const P
             swap = (q & 1u) != 0;                                      // parity(pf) = lsb of igray(pf)
         }
         // children of natural node m sit at columns 2q + {0, 1}; `swap` exchanges them: resolved by addressing
-        float* o_lo = out_b + static_cast<long long>(k0) * P + 2 * q + (swap ? 1 : 0);
-        float* o_hi = out_b + static_cast<long long>(k0) * P + 2 * q + (swap ? 0 : 1);
+        const int col_lo = static_cast<int>(2 * q) + (swap ? 1 : 0);
+        const int col_hi = static_cast<int>(2 * q) + (swap ? 0 : 1);
+        float* o_lo = out_b + static_cast<long long>(k0) * P + col_lo;
+        float* o_hi = out_b + static_cast<long long>(k0) * P + col_hi;
         const int nv = T - k0;                                         // rows r < nv exist
+        if constexpr (extended) {
+            if (ep.node_stats) {                                       // statistics of the raw coefficients
+                if (ts.col[0] != col_lo) {                             // never taken when stats_simple
+                    flush_node_stats(ep, P, ts);
+                    ts.col[0] = col_lo; ts.col[1] = col_hi;
+                }
+#pragma unroll
+                for (int r = 0; r < RL; ++r)
+                    if (r < nv) {
+                        ts.s[0] += lo[r]; ts.q[0] = fmaf(lo[r], lo[r], ts.q[0]); ts.m[0] = fmaxf(ts.m[0], fabsf(lo[r]));
+                        ts.s[1] += hi[r]; ts.q[1] = fmaf(hi[r], hi[r], ts.q[1]); ts.m[1] = fmaxf(ts.m[1], fabsf(hi[r]));
+                    }
+            }
+            if (ep.node_scale) {
+                const float s_lo = __ldg(ep.node_scale + col_lo), s_hi = __ldg(ep.node_scale + col_hi);
+#pragma unroll
+                for (int r = 0; r < RL; ++r) { lo[r] *= s_lo; hi[r] *= s_hi; }
+            }
+        }
         if (two) {
+            float sl = 1.f, sh = 1.f, dl = 0.f;                        // sign channel: (s - mean1) * rstd1
+            if (extended && ep.normalize) { sl = ep.nrstd[1]; sh = ep.nrstd[1]; dl = -ep.nmean[1] * ep.nrstd[1]; }
 #pragma unroll
             for (int r = 0; r < RL; ++r)
                 if (r < nv) {
-                    __stcs(o_lo + ch1 + r * P, lo[r] < 0.f ? -1.f : 1.f);      // r * P < T * P < 2^31
-                    __stcs(o_hi + ch1 + r * P, hi[r] < 0.f ? -1.f : 1.f);
+                    const float a = lo[r] < 0.f ? -1.f : 1.f, d = hi[r] < 0.f ? -1.f : 1.f;
+                    if (extended && ep.feat_moments) { ts.fs[1] += a + d; ts.fq[1] += 2.f; }
+                    if (!extended || ep.store) {
+                        __stcs(o_lo + ch1 + r * P, extended ? fmaf(a, sl, dl) : a);   // r * P < T * P < 2^31
+                        __stcs(o_hi + ch1 + r * P, extended ? fmaf(d, sh, dl) : d);
+                    }
                 }
         }
         if (mode == 1) {
@@ -405,13 +485,31 @@ __device__ __forceinline__ void last_level(const float* __restrict__ in, const P
 #pragma unroll
             for (int r = 0; r < RL; ++r) { lo[r] = log_power(lo[r], ep.power, off, false); hi[r] = log_power(hi[r], ep.power, off, false); }
         }
+        if constexpr (extended) {
+            if (ep.feat_moments) {
 #pragma unroll
-        for (int r = 0; r < RL; ++r)
-            if (r < nv) {
-                __stcs(o_lo + r * P, lo[r]);
-                __stcs(o_hi + r * P, hi[r]);
+                for (int r = 0; r < RL; ++r)
+                    if (r < nv) {
+                        ts.fs[0] += lo[r] + hi[r];
+                        ts.fq[0] = fmaf(lo[r], lo[r], fmaf(hi[r], hi[r], ts.fq[0]));
+                    }
             }
+            if (ep.normalize) {
+                const float rs = ep.nrstd[0], dm = -ep.nmean[0] * ep.nrstd[0];
+#pragma unroll
+                for (int r = 0; r < RL; ++r) { lo[r] = fmaf(lo[r], rs, dm); hi[r] = fmaf(hi[r], rs, dm); }
+            }
+        }
+        if (!extended || ep.store) {
+#pragma unroll
+            for (int r = 0; r < RL; ++r)
+                if (r < nv) {
+                    __stcs(o_lo + r * P, lo[r]);
+                    __stcs(o_hi + r * P, hi[r]);
+                }
+        }
     }
+    if (extended && ep.node_stats && !ep.stats_simple) flush_node_stats(ep, P, ts);
 }
 
 // Stage chunk j of the frame (with the frame's own reflect padding) into `buf` with cp.async.
@@ -456,7 +554,7 @@ __device__ __forceinline__ void issue_chunk(const float* __restrict__ xg, float*
     cp_async_commit();
 }
 
-template <int F, int R1, int RA, int RB, int RLA, int RLB, bool LAT>
+template <int F, int R1, int RA, int RB, int RLA, int RLB, bool LAT, bool EXT>
 __global__ void __launch_bounds__(kThreads, 2)
 wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B, float* __restrict__ out,
                 const __grid_constant__ WptPlan plan, const __grid_constant__ Coefs<F> cf,
@@ -481,6 +579,10 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
     for (int m = 0; m < F; ++m) t1[m] = half ? cf.hi[m] : cf.lo[m];
     bool prefetched = false;
     bool first = true;
+    ThreadStats ts;
+    ts.s[0] = ts.s[1] = ts.q[0] = ts.q[1] = ts.m[0] = ts.m[1] = 0.f;
+    ts.fs[0] = ts.fs[1] = ts.fq[0] = ts.fq[1] = 0.f;
+    ts.col[0] = ts.col[1] = -1;
 
     for (long long wk = blockIdx.x; wk < 2 * B; wk += gridDim.x) {
         const long long b = wk >> 1;
@@ -507,16 +609,24 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
             // the level-1 node is the output: epilogue straight from shared memory (rare configuration)
             if (nb < 2 * B) { issue_chunk<F>(x + (nb >> 1) * x_row_stride, buf0, 0, plan); prefetched = true; }
             const bool square = ep.square != 0;
+            if (EXT && ep.node_stats) { ts.col[0] = half; ts.col[1] = half; }      // slot 1 stays empty (adds zeros)
             for (int e = threadIdx.x; e < T; e += kThreads) {
-                const float c = regA[padl + e];
+                float c = regA[padl + e];
+                if (EXT && ep.node_stats) { ts.s[0] += c; ts.q[0] = fmaf(c, c, ts.q[0]); ts.m[0] = fmaxf(ts.m[0], fabsf(c)); }
+                if (EXT && ep.node_scale) c *= __ldg(ep.node_scale + half);
                 float* dst = out_b + static_cast<long long>(e) * P + half;
-                if (ep.log_scale) {
-                    st_cs(dst, log_power(c, ep.power, ep.log_offset, square));
-                    if (C == 2) st_cs(dst + static_cast<long long>(T) * P, c < 0.f ? -1.f : 1.f);
-                } else {
-                    st_cs(dst, c);
+                float v = ep.log_scale ? log_power(c, ep.power, ep.log_offset, square) : c;
+                if (EXT && ep.feat_moments) { ts.fs[0] += v; ts.fq[0] = fmaf(v, v, ts.fq[0]); }
+                if (EXT && ep.normalize) v = (v - ep.nmean[0]) * ep.nrstd[0];
+                if (!EXT || ep.store) st_cs(dst, v);
+                if (C == 2) {
+                    float sg = c < 0.f ? -1.f : 1.f;
+                    if (EXT && ep.feat_moments) { ts.fs[1] += sg; ts.fq[1] += 1.f; }
+                    if (EXT && ep.normalize) sg = (sg - ep.nmean[1]) * ep.nrstd[1];
+                    if (!EXT || ep.store) st_cs(dst + static_cast<long long>(T) * P, sg);
                 }
             }
+            if (EXT && ep.node_stats) flush_node_stats(ep, P, ts);
             continue;
         }
         // ---------------------------------------------------------------- levels 2 .. L as planned passes
@@ -532,12 +642,16 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
                     issue_chunk<F>(x + (nb >> 1) * x_row_stride, buf0, 0, plan);
                     prefetched = true;
                 }
-                if (ps.rsel == 0) last_level<F, RLA, LAT>(smem + ps.in_off, ps, T, half_base, out_b, P, cf, ep);
-                else last_level<F, RLB, LAT>(smem + ps.in_off, ps, T, half_base, out_b, P, cf, ep);
+                if (ps.rsel == 0) last_level<F, RLA, LAT, EXT>(smem + ps.in_off, ps, T, half_base, out_b, P, cf, ep, ts);
+                else last_level<F, RLB, LAT, EXT>(smem + ps.in_off, ps, T, half_base, out_b, P, cf, ep, ts);
             }
         }
     }
     cp_async_wait<0>();
+    if constexpr (EXT) {
+        if (ep.node_stats) flush_node_stats(ep, P, ts);   // stats_simple: the one flush of the launch
+        if (ep.feat_moments) flush_feat_moments(ep, C, ts);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -678,7 +792,7 @@ struct PlanReport {
     int pass_r[kMaxPasses];          // item size chosen for each pass
 };
 
-template <int F, int R1, int RA, int RB, int RLA, int RLB, bool LAT>
+template <int F, int R1, int RA, int RB, int RLA, int RLB, bool LAT, bool EXT>
 static int launch(const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* out, int L,
                   const double* dec_lo, const LatticeInfo& lat, const Epilogue& ep, cudaStream_t stream,
                   PlanReport* report) {
@@ -706,13 +820,20 @@ static int launch(const float* x, int64_t B, int64_t N, int64_t x_row_stride, fl
         }
         return AFD_OK;
     }
+    Epilogue epk = ep;
+    {
+        int last_passes = 0, parents = 0;
+        for (int i = 0; i < plan.npass; ++i)
+            if (plan.pass[i].kind == 1) { ++last_passes; parents = plan.pass[i].parents; }
+        epk.stats_simple = (last_passes == 1 && parents <= kThreads && kThreads % parents == 0) ? 1 : 0;
+    }
     Coefs<F> cf;
     for (int k = 0; k < F; ++k) {
         cf.lo[k] = static_cast<float>(dec_lo[k]);
         cf.hi[k] = static_cast<float>(((k & 1) ? 1.0 : -1.0) * dec_lo[F - 1 - k]);   // dec_hi[k] = (-1)^(k+1) dec_lo[F-1-k]
     }
     for (int m = 0; m < F / 2; ++m) cf.t[m] = LAT ? static_cast<float>(lat.tan_theta[m]) : 0.f;
-    auto kern = wpt_tree_kernel<F, R1, RA, RB, RLA, RLB, LAT>;
+    auto kern = wpt_tree_kernel<F, R1, RA, RB, RLA, RLB, LAT, EXT>;
     static thread_local bool configured[16] = {false};  // per device
     int dev = 0, sms = kNumSmsFallback;
     AFD_CUDA_TRY(cudaGetDevice(&dev));
@@ -738,7 +859,7 @@ static int launch(const float* x, int64_t B, int64_t N, int64_t x_row_stride, fl
     if (ctas == 1) grid = sms / 2 * 2;
     if (grid > 2 * B) grid = 2 * B;
     kern<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(x, static_cast<long long>(x_row_stride),
-                                                                   static_cast<long long>(B), out, plan, cf, ep);
+                                                                   static_cast<long long>(B), out, plan, cf, epk);
     AFD_CUDA_TRY(cudaGetLastError());
     return AFD_OK;
 }
@@ -751,46 +872,50 @@ constexpr int pick_rd(int F) { return F <= 40 ? 10 : 6; }           // direct fo
 // second last-level item size: a quarter of the leaf length of the headline shape (N = 22050, level 8: T ~ 85 + F)
 constexpr int pick_rlb(int F) { return 2 * ((85 + F + 7) / 8); }
 
-template <int F>
+template <int F, bool EXT>
 static int dispatch_one(const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* out, int L,
                         const double* dec_lo, const Epilogue& ep, cudaStream_t stream, PlanReport* report) {
     LatticeInfo lat{};
     lat.scale = 1.0;
     if constexpr (F <= 32) {
         if (lattice_factor(dec_lo, F, &lat) == AFD_OK && lat.usable)
-            return launch<F, pick_r1(F), 22, 26, 14, pick_rlb(F), true>(x, B, N, x_row_stride, out, L, dec_lo, lat, ep, stream, report);
-        return launch<F, pick_r1(F), 14, 10, 14, 10, false>(x, B, N, x_row_stride, out, L, dec_lo, lat, ep, stream, report);
+            return launch<F, pick_r1(F), 22, 26, 14, pick_rlb(F), true, EXT>(x, B, N, x_row_stride, out, L, dec_lo, lat, ep, stream, report);
+        return launch<F, pick_r1(F), 14, 10, 14, 10, false, EXT>(x, B, N, x_row_stride, out, L, dec_lo, lat, ep, stream, report);
     } else {
-        return launch<F, pick_r1(F), pick_rd(F), pick_rd(F), pick_rd(F), pick_rd(F), false>(
+        return launch<F, pick_r1(F), pick_rd(F), pick_rd(F), pick_rd(F), pick_rd(F), false, EXT>(
             x, B, N, x_row_stride, out, L, dec_lo, lat, ep, stream, report);
     }
 }
 
 
-// Filter lengths are compiled in four groups (separate translation units, built in parallel).
+// Filter lengths are compiled in four groups, each for the plain (afd_wpt_forward) and the extended
+// (afd_wpt_forward_ex) epilogue: eight translation units, built in parallel.
 using WptGroupFn = int (*)(int F, const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* out, int L,
                            const double* dec_lo, const Epilogue& ep, cudaStream_t stream, PlanReport* report);
-int wpt_group0(int F, const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* out, int L,
-               const double* dec_lo, const Epilogue& ep, cudaStream_t stream, PlanReport* report);   // F = 2 .. 16
-int wpt_group1(int F, const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* out, int L,
-               const double* dec_lo, const Epilogue& ep, cudaStream_t stream, PlanReport* report);   // F = 18 .. 32
-int wpt_group2(int F, const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* out, int L,
-               const double* dec_lo, const Epilogue& ep, cudaStream_t stream, PlanReport* report);   // F = 34 .. 48
-int wpt_group3(int F, const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* out, int L,
-               const double* dec_lo, const Epilogue& ep, cudaStream_t stream, PlanReport* report);   // F = 50 .. 64
+#define AFD_WPT_GROUP_DECL(NAME)                                                                                     \
+    int NAME(int F, const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* out, int L,                   \
+             const double* dec_lo, const Epilogue& ep, cudaStream_t stream, PlanReport* report);
+AFD_WPT_GROUP_DECL(wpt_group0)     // F = 2 .. 16
+AFD_WPT_GROUP_DECL(wpt_group1)     // F = 18 .. 32
+AFD_WPT_GROUP_DECL(wpt_group2)     // F = 34 .. 48
+AFD_WPT_GROUP_DECL(wpt_group3)     // F = 50 .. 64
+AFD_WPT_GROUP_DECL(wpt_xgroup0)    // the same with the extended epilogue
+AFD_WPT_GROUP_DECL(wpt_xgroup1)
+AFD_WPT_GROUP_DECL(wpt_xgroup2)
+AFD_WPT_GROUP_DECL(wpt_xgroup3)
 
-#define AFD_WPT_GROUP(NAME, F0)                                                                                      \
+#define AFD_WPT_GROUP(NAME, F0, EXT)                                                                                 \
     int NAME(int F, const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* out, int L,                   \
              const double* dec_lo, const Epilogue& ep, cudaStream_t stream, PlanReport* report) {                    \
         switch (F) {                                                                                                 \
-            case F0: return dispatch_one<F0>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report);             \
-            case F0 + 2: return dispatch_one<F0 + 2>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report);     \
-            case F0 + 4: return dispatch_one<F0 + 4>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report);     \
-            case F0 + 6: return dispatch_one<F0 + 6>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report);     \
-            case F0 + 8: return dispatch_one<F0 + 8>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report);     \
-            case F0 + 10: return dispatch_one<F0 + 10>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report);   \
-            case F0 + 12: return dispatch_one<F0 + 12>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report);   \
-            case F0 + 14: return dispatch_one<F0 + 14>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report);   \
+            case F0: return dispatch_one<F0, EXT>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report);        \
+            case F0 + 2: return dispatch_one<F0 + 2, EXT>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report); \
+            case F0 + 4: return dispatch_one<F0 + 4, EXT>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report); \
+            case F0 + 6: return dispatch_one<F0 + 6, EXT>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report); \
+            case F0 + 8: return dispatch_one<F0 + 8, EXT>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report); \
+            case F0 + 10: return dispatch_one<F0 + 10, EXT>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report); \
+            case F0 + 12: return dispatch_one<F0 + 12, EXT>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report); \
+            case F0 + 14: return dispatch_one<F0 + 14, EXT>(x, B, N, x_row_stride, out, L, dec_lo, ep, stream, report); \
         }                                                                                                            \
         return fail(AFD_ERR_INVALID_ARG, "unsupported filter length %d", F);                                         \
     }

@@ -55,10 +55,36 @@ def wpt_out_len(n: int, filt_len: int, level: int) -> int:
     return out.value
 
 
+def _norm_array(norm, channels: int):
+    """(mean, std) scalars / per-channel sequences -> ctypes float[C][2] for the fused Normalize epilogue."""
+    if norm is None:
+        return None
+    mean, std = norm
+    mean = torch.as_tensor(mean, dtype=torch.float32).reshape(-1).tolist()
+    std = torch.as_tensor(std, dtype=torch.float32).reshape(-1).tolist()
+    if len(mean) == 1:
+        mean = mean * channels
+    if len(std) == 1:
+        std = std * channels
+    if len(mean) != channels or len(std) != channels:
+        raise ValueError(f"normalisation needs 1 or {channels} mean/std values, got {len(mean)}/{len(std)}")
+    flat = []
+    for m, sd in zip(mean, std):
+        flat += [m, sd]
+    return (ctypes.c_float * (2 * channels))(*flat)
+
+
 def wavelet_packet_features(pt_data: torch.Tensor, wavelet, max_lev: int = 8, log_scale: bool = False,
                             loss_less: bool = False, power: float = 2.0, order: str = "freq",
-                            log_offset: float = 1e-12) -> torch.Tensor:
-    """Fused packet transform; returns contiguous ``[B, C, T, P]`` (C = 2 only with log_scale and loss_less)."""
+                            log_offset: float = 1e-12, *, node_scale: Optional[torch.Tensor] = None,
+                            norm=None, node_stats: Optional[torch.Tensor] = None,
+                            feat_moments: Optional[torch.Tensor] = None, store: bool = True):
+    """Fused packet transform; returns contiguous ``[B, C, T, P]`` (C = 2 only with log_scale and loss_less).
+
+    Keyword-only extras map one to one onto ``afd_wpt_forward_ex`` (include/afd_b200.h): ``node_scale`` fp32
+    ``[P]`` (block norm), ``norm=(mean, std)`` fused Normalize, ``node_stats`` fp64 ``[3, P]`` and
+    ``feat_moments`` fp64 ``[C, 2]`` accumulators; ``store=False`` skips the feature tensor (returns ``None``).
+    """
     x = _as_frames(pt_data, "wavelet_packet_features")
     wav = get_wavelet(wavelet)
     taps = [float(v) for v in wav.dec_lo]
@@ -67,16 +93,105 @@ def wavelet_packet_features(pt_data: torch.Tensor, wavelet, max_lev: int = 8, lo
     T = wpt_out_len(N, F, max_lev)
     C = 2 if (log_scale and loss_less) else 1
     P = 1 << max_lev
-    out = torch.empty((B, C, T, P), dtype=torch.float32, device=x.device)
+    extended = node_scale is not None or norm is not None or node_stats is not None or feat_moments is not None
+    if not store and node_stats is None and feat_moments is None:
+        raise ValueError("store=False needs node_stats or feat_moments to accumulate into")
+    out = torch.empty((B, C, T, P), dtype=torch.float32, device=x.device) if store else None
     c_taps = (ctypes.c_double * F)(*taps)
+    order_id = _lib.AFD_ORDER_FREQ if order == "freq" else _lib.AFD_ORDER_NATURAL
+    stride = x.stride(0) if B > 1 else N
+    out_ptr = ctypes.c_void_p(out.data_ptr()) if store else None
+
+    def _dev(t, dtype, shape, what):
+        if t is None:
+            return None
+        if t.device != x.device or t.dtype != dtype or tuple(t.shape) != shape or not t.is_contiguous():
+            raise ValueError(f"{what} must be a contiguous {dtype} tensor of shape {shape} on {x.device}")
+        return ctypes.c_void_p(t.data_ptr())
+
     with torch.cuda.device(x.device):
-        rc = _lib.load().afd_wpt_forward(
-            ctypes.c_void_p(x.data_ptr()), B, N, x.stride(0) if B > 1 else N, c_taps, F, max_lev,
-            _lib.AFD_ORDER_FREQ if order == "freq" else _lib.AFD_ORDER_NATURAL,
-            float(power), int(bool(log_scale)), float(log_offset), int(bool(loss_less)),
-            ctypes.c_void_p(out.data_ptr()), None, _stream_ptr(x.device))
-    _lib.check("afd_wpt_forward", rc)
+        if not extended:
+            rc = _lib.load().afd_wpt_forward(
+                ctypes.c_void_p(x.data_ptr()), B, N, stride, c_taps, F, max_lev, order_id,
+                float(power), int(bool(log_scale)), float(log_offset), int(bool(loss_less)),
+                out_ptr, None, _stream_ptr(x.device))
+            _lib.check("afd_wpt_forward", rc)
+        else:
+            rc = _lib.load().afd_wpt_forward_ex(
+                ctypes.c_void_p(x.data_ptr()), B, N, stride, c_taps, F, max_lev, order_id,
+                float(power), int(bool(log_scale)), float(log_offset), int(bool(loss_less)),
+                _dev(node_scale, torch.float32, (P,), "node_scale"), _norm_array(norm, C),
+                _dev(node_stats, torch.float64, (3, P), "node_stats"),
+                _dev(feat_moments, torch.float64, (C, 2), "feat_moments"),
+                out_ptr, None, _stream_ptr(x.device))
+            _lib.check("afd_wpt_forward_ex", rc)
     return out
+
+
+def graycode_paths(level: int) -> list[str]:
+    """Leaf paths in frequency order (ptwt get_level / reference wavelet_math.py:185)."""
+    order = ["a", "d"]
+    for _ in range(level - 1):
+        order = ["a" + p for p in order] + ["d" + p for p in order[::-1]]
+    return order
+
+
+class NodeStatsTable:
+    """Running count / mean / M2 of every leaf node at once (fp64 ``[P]`` on the device).
+
+    One table stands in for the 2^level ``WelfordEstimator`` objects the reference keeps in its
+    ``block_norm_dict`` (wavelet_math.py:194-200, data_loader.py:27-71): batches are merged with Chan's parallel
+    update from the per-node sums the kernel accumulates, which yields the same mean and ``sqrt(m2 / count)``.
+    """
+
+    def __init__(self, packets: int, device):
+        self.count = 0
+        self.mean = torch.zeros(packets, dtype=torch.float64, device=device)
+        self.m2 = torch.zeros(packets, dtype=torch.float64, device=device)
+
+    def merge_sums(self, s: torch.Tensor, q: torch.Tensor, n: int) -> None:
+        mean_b = s / n
+        m2_b = torch.clamp(q - s * mean_b, min=0)
+        tot = self.count + n
+        delta = mean_b - self.mean
+        self.m2 += m2_b + delta * delta * (self.count * n / tot)
+        self.mean += delta * (n / tot)
+        self.count = tot
+
+
+class NodeStats:
+    """One node's view of a ``NodeStatsTable`` with the ``WelfordEstimator`` surface (count, mean, m2, finalize)."""
+
+    def __init__(self, table: NodeStatsTable, index: int):
+        self.table = table
+        self.index = index
+
+    @property
+    def count(self) -> torch.Tensor:
+        return torch.tensor([float(self.table.count)], device=self.table.mean.device)
+
+    @property
+    def mean(self) -> torch.Tensor:
+        return self.table.mean[self.index:self.index + 1].float()
+
+    @property
+    def m2(self) -> torch.Tensor:
+        return self.table.m2[self.index:self.index + 1].float()
+
+    def finalize(self):
+        return self.mean, torch.sqrt(self.table.m2[self.index:self.index + 1] / self.table.count).float()
+
+
+def _stats_table(block_norm_dict: dict, level: int, device) -> NodeStatsTable:
+    """The table behind ``block_norm_dict`` (created, and the per-path views filled in, on first use)."""
+    for v in block_norm_dict.values():
+        if isinstance(v, NodeStats):
+            return v.table
+        break
+    table = NodeStatsTable(1 << level, device)
+    for p, key in enumerate(graycode_paths(level)):
+        block_norm_dict[key] = NodeStats(table, p)
+    return table
 
 
 def compute_pytorch_packet_representation(
@@ -89,71 +204,42 @@ def compute_pytorch_packet_representation(
     block_norm: bool = False,
     compute_welford: bool = False,
     block_norm_dict=None,
+    *,
+    norm=None,
+    feat_moments: Optional[torch.Tensor] = None,
+    store: bool = True,
 ) -> tuple[torch.Tensor, dict]:
     """Create a packet image ``[B, C, T, P]`` (reference wavelet_math.py:167-220).
 
-    ``block_norm`` (per-node division by the batch-wide max |c|, reference :202-203) and the per-node Welford
-    statistics (reference :194-200) are evaluated on the raw coefficients when requested; the default training
-    path discards both (``_`` at reference train_classifier.py:966), so the fused kernel is the fast path.
+    The keyword-only extras are this package's additions: ``norm=(mean, std)`` fuses the reference's separate
+    ``Normalize`` step into the epilogue, ``feat_moments`` (fp64 ``[C, 2]``) accumulates the feature sum / sum of
+    squares that ``calc_normalization`` needs, ``store=False`` computes statistics only.
+
+    ``compute_welford`` (per-node running mean / M2, reference :194-200) costs nothing extra: the kernel
+    accumulates every node's sum, sum of squares and max |c| while it writes the features.  ``block_norm``
+    (``node / max|node|`` over the batch, reference :202-203) needs the maxima before the epilogue, so it runs a
+    statistics-only launch first (no feature tensor is written) and a second launch with the per-node scale.
     """
     if block_norm_dict is None:
         block_norm_dict = {}
+    extras = dict(norm=norm, feat_moments=feat_moments, store=store)
     if not block_norm and not compute_welford:
-        return wavelet_packet_features(pt_data, wavelet, max_lev, log_scale, loss_less, power), block_norm_dict
+        return (wavelet_packet_features(pt_data, wavelet, max_lev, log_scale, loss_less, power, **extras),
+                block_norm_dict)
 
-    # Options that need the raw per-node coefficients: one fused launch for the coefficients, then the
-    # statistics / scaling as whole-tensor ops (256 nodes at once instead of the reference's python node loop).
-    raw = wavelet_packet_features(pt_data, wavelet, max_lev, False, False, power)[:, 0]  # [B, T, P]
-    if compute_welford:
-        _update_node_stats(block_norm_dict, raw, max_lev)
+    x = _as_frames(pt_data, "compute_pytorch_packet_representation")
+    P = 1 << max_lev
+    stats = torch.zeros((3, P), dtype=torch.float64, device=x.device)
     if block_norm:
-        raw = raw / raw.abs().amax(dim=(0, 1), keepdim=True)
-    if log_scale:
-        wp_log = torch.log(raw.abs().pow(power) + 1e-12)
-        if loss_less:
-            sign = ((raw < 0).to(torch.float32) * (-1) + 0.5) * 2
-            return torch.stack([wp_log, sign], 1), block_norm_dict
-        return wp_log.unsqueeze(1), block_norm_dict
-    return raw.unsqueeze(1), block_norm_dict
-
-
-def graycode_paths(level: int) -> list[str]:
-    """Leaf paths in frequency order (ptwt get_level / reference wavelet_math.py:185)."""
-    order = ["a", "d"]
-    for _ in range(level - 1):
-        order = ["a" + p for p in order] + ["d" + p for p in order[::-1]]
-    return order
-
-
-class NodeStats:
-    """Per-node running mean / M2 with the ``WelfordEstimator`` surface (reference data_loader.py:27-71)."""
-
-    def __init__(self):
-        self.count = None
-        self.mean = None
-        self.m2 = None
-
-    def finalize(self):
-        return self.mean, torch.sqrt(self.m2 / self.count)
-
-
-def _update_node_stats(stats: dict, raw: torch.Tensor, level: int) -> None:
-    """Chan's parallel update of every node's (count, mean, M2) in three tensor ops."""
-    n_b = raw.shape[0] * raw.shape[1]
-    mean_b = raw.mean(dim=(0, 1))
-    m2_b = ((raw - mean_b) ** 2).sum(dim=(0, 1))
-    for p, key in enumerate(graycode_paths(level)):
-        st = stats.get(key)
-        if st is None:
-            st = stats[key] = NodeStats()
-            st.count = torch.zeros(1, device=raw.device)
-            st.mean = torch.zeros(1, device=raw.device)
-            st.m2 = torch.zeros(1, device=raw.device)
-        tot = st.count + n_b
-        delta = mean_b[p:p + 1] - st.mean
-        st.m2 = st.m2 + m2_b[p:p + 1] + delta * delta * st.count * n_b / tot
-        st.mean = st.mean + delta * n_b / tot
-        st.count = tot
+        wavelet_packet_features(x, wavelet, max_lev, False, False, power, node_stats=stats, store=False)
+        scale = (1.0 / stats[2]).to(torch.float32)
+        out = wavelet_packet_features(x, wavelet, max_lev, log_scale, loss_less, power, node_scale=scale, **extras)
+    else:
+        out = wavelet_packet_features(x, wavelet, max_lev, log_scale, loss_less, power, node_stats=stats, **extras)
+    if compute_welford:
+        n = x.shape[0] * wpt_out_len(x.shape[1], len(get_wavelet(wavelet).dec_lo), max_lev)
+        _stats_table(block_norm_dict, max_lev, x.device).merge_sums(stats[0], stats[1], n)
+    return out, block_norm_dict
 
 
 class Packets(torch.nn.Module):
@@ -179,13 +265,23 @@ class Packets(torch.nn.Module):
         self.block_norm = block_norm
         self.compute_welford = compute_welford
         self.block_norm_dict = block_norm_dict
+        self.fused_norm = None       # (mean, std): apply the reference's Normalize inside the kernel (fuse_normalize)
+        self.feat_moments = None     # fp64 [C, 2] accumulator filled by calc_normalization
+        self.store = True
+
+    @property
+    def channels(self) -> int:
+        return 2 if (self.log_scale and self.loss_less) else 1
 
     def forward(self, pt_data: torch.Tensor) -> tuple[torch.Tensor, dict]:
         packets, block_norm_dict = compute_pytorch_packet_representation(
             pt_data, self.wavelet, self.max_lev, self.log_scale, self.loss_less, self.power,
             block_norm=self.block_norm, compute_welford=self.compute_welford,
             block_norm_dict=self.block_norm_dict,
+            norm=self.fused_norm, feat_moments=self.feat_moments, store=self.store,
         )
+        if packets is None:
+            return None, block_norm_dict
         return packets.permute(0, 1, 3, 2), block_norm_dict
 
 
@@ -197,17 +293,37 @@ def stft_out_shape(n: int, n_fft: int, hop: int) -> tuple[int, int]:
 
 
 def stft_power_features(x: torch.Tensor, n_fft: int = 511, hop_length: int = 220, power: float = 2.0,
-                        log_scale: bool = False, log_offset: float = 1e-12) -> torch.Tensor:
-    """Fused STFT power spectrogram; returns contiguous ``[B, 1, frames, bins]``."""
+                        log_scale: bool = False, log_offset: float = 1e-12, *, norm=None,
+                        feat_moments: Optional[torch.Tensor] = None, store: bool = True):
+    """Fused STFT power spectrogram; returns contiguous ``[B, 1, frames, bins]``.
+
+    ``norm`` / ``feat_moments`` (fp64 ``[1, 2]``) / ``store`` as in ``wavelet_packet_features``
+    (``afd_stft_power_ex``)."""
     xf = _as_frames(x, "stft_power_features")
     B, N = xf.shape
     frames, bins = stft_out_shape(N, n_fft, hop_length)
-    out = torch.empty((B, 1, frames, bins), dtype=torch.float32, device=xf.device)
+    if not store and feat_moments is None:
+        raise ValueError("store=False needs feat_moments to accumulate into")
+    out = torch.empty((B, 1, frames, bins), dtype=torch.float32, device=xf.device) if store else None
+    out_ptr = ctypes.c_void_p(out.data_ptr()) if store else None
+    stride = xf.stride(0) if B > 1 else N
     with torch.cuda.device(xf.device):
-        rc = _lib.load().afd_stft_power(
-            ctypes.c_void_p(xf.data_ptr()), B, N, xf.stride(0) if B > 1 else N, n_fft, hop_length, float(power),
-            int(bool(log_scale)), float(log_offset), ctypes.c_void_p(out.data_ptr()), _stream_ptr(xf.device))
-    _lib.check("afd_stft_power", rc)
+        if norm is None and feat_moments is None:
+            rc = _lib.load().afd_stft_power(
+                ctypes.c_void_p(xf.data_ptr()), B, N, stride, n_fft, hop_length, float(power),
+                int(bool(log_scale)), float(log_offset), out_ptr, _stream_ptr(xf.device))
+            _lib.check("afd_stft_power", rc)
+        else:
+            mom = None
+            if feat_moments is not None:
+                if (feat_moments.device != xf.device or feat_moments.dtype != torch.float64
+                        or feat_moments.numel() != 2 or not feat_moments.is_contiguous()):
+                    raise ValueError(f"feat_moments must be a contiguous float64 tensor of 2 elements on {xf.device}")
+                mom = ctypes.c_void_p(feat_moments.data_ptr())
+            rc = _lib.load().afd_stft_power_ex(
+                ctypes.c_void_p(xf.data_ptr()), B, N, stride, n_fft, hop_length, float(power),
+                int(bool(log_scale)), float(log_offset), _norm_array(norm, 1), mom, out_ptr, _stream_ptr(xf.device))
+            _lib.check("afd_stft_power_ex", rc)
     return out
 
 
@@ -223,9 +339,16 @@ class STFTLayer(torch.nn.Module):
         self.log_scale = log_scale
         self.log_offset = log_offset     # stored but, like the reference (:66), the literal 1e-12 is applied
         self.block_norm_dict = None
+        self.fused_norm = None
+        self.feat_moments = None
+        self.store = True
+        self.channels = 1
 
     def forward(self, input: torch.Tensor) -> tuple[torch.Tensor, None]:
-        spec = stft_power_features(input, self.n_fft, self.hop_length, self.power, self.log_scale, 1e-12)
+        spec = stft_power_features(input, self.n_fft, self.hop_length, self.power, self.log_scale, 1e-12,
+                                   norm=self.fused_norm, feat_moments=self.feat_moments, store=self.store)
+        if spec is None:
+            return None, None
         return spec.permute(0, 1, 3, 2), None
 
 
@@ -243,14 +366,24 @@ class Normalize(torch.nn.Module):
         return (x - mean) / std
 
 
+def _opt(args, name: str, default):
+    """Optional flag of the reference's DotDict (utils.py:321-395: attribute access is dict lookup, so a missing
+    key may raise KeyError instead of AttributeError)."""
+    try:
+        return getattr(args, name)
+    except (AttributeError, KeyError):
+        return default
+
+
 def get_transforms(args, features: str, device: str, normalization: bool, pbar: bool = False,
-                   verbose: bool = True) -> tuple[torch.nn.Sequential, torch.nn.Sequential]:
+                   verbose: bool = True, norm_batches=None) -> tuple[torch.nn.Sequential, torch.nn.Sequential]:
     """Initialize transformations and normalize (reference wavelet_math.py:266-384).
 
     ``args`` needs the reference's flag names: transform, num_of_scales, hop_length, log_scale, power, wavelet,
-    loss_less ("True"/"False" strings), features, block_norm, mean, std.  Normalisation statistics are taken
-    from ``args.mean`` / ``args.std`` (the reference's dataset pass, calc_normalization, is out of scope here;
-    see ``normalization_stats`` for the streaming equivalent on tensors).
+    loss_less ("True"/"False" strings), features, block_norm, mean, std.  With ``normalization=True`` the
+    statistics are computed by ``calc_normalization`` over ``norm_batches`` -- an iterable of audio batches
+    standing in for the reference's training-set DataLoader (:396-424; dataset and wav I/O are out of scope
+    here); otherwise ``args.mean`` / ``args.std`` are used (:368-371).
     """
     if features not in ("none", None):
         raise NotImplementedError("only features='none' is on the accelerated path (lfcc/delta are out of scope)")
@@ -270,22 +403,83 @@ def get_transforms(args, features: str, device: str, normalization: bool, pbar: 
             power=args.power,
             block_norm_dict=None,
             block_norm=False,
-            compute_welford=False,   # reference hard-codes True (:304) and discards the result
+            # the reference hard-codes True (:304) and the trainer discards the result (train_classifier.py:966);
+            # here the statistics are fused into the kernel and opt-in, to keep tiny batches launch-lean
+            compute_welford=bool(_opt(args, "compute_welford", False)),
         )
     else:
         raise ValueError(f"unknown transform '{args.transform}'")
     transforms = torch.nn.Sequential(transform)
-    if getattr(args, "block_norm", False):
-        raise NotImplementedError("block_norm needs the reference's dataset pass (calc_normalization)")
-    mean = torch.as_tensor(args.mean, dtype=torch.float32, device=device)
-    std = torch.as_tensor(args.std, dtype=torch.float32, device=device)
+    block_norm = bool(_opt(args, "block_norm", False))
+    welford_dict = None
+    if normalization:
+        if norm_batches is None:
+            raise ValueError("normalization=True needs norm_batches (audio batches of the training set)")
+        welford_dict, mean, std = calc_normalization(transforms, norm_batches)
+    else:
+        mean = torch.as_tensor(args.mean, dtype=torch.float32, device=device)
+        std = torch.as_tensor(args.std, dtype=torch.float32, device=device)
+    if block_norm:                                        # reference :373-378
+        if args.transform != "packets":
+            raise ValueError("block_norm is a packet option")
+        mean, std = 0.0, 1.0
+        transform.block_norm_dict = welford_dict
+        transform.compute_welford = False
+        transform.block_norm = True
     normalize = torch.nn.Sequential(Normalize(mean, std))
     return transforms, normalize
 
 
+def calc_normalization(transforms: torch.nn.Sequential, audio_batches) -> tuple:
+    """Mean / std of the features over ``audio_batches`` (reference wavelet_math.py:387-452, minus the dataset
+    plumbing): returns ``(welford_dict, mean, std)`` like the reference, mean / std per channel.
+
+    One statistics-only launch per batch: the kernels accumulate the feature sum / sum of squares in fp64 on the
+    device (``feat_moments``) and never write the feature tensor, so the pass reads 88 KB per frame and writes
+    nothing."""
+    tr = transforms[0]
+    dev = None
+    moments, count, welford_dict = None, 0, None
+    saved = (tr.feat_moments, tr.store, tr.fused_norm)
+    try:
+        for batch in audio_batches:
+            x = batch["audio"] if isinstance(batch, dict) else batch
+            if not x.is_cuda:
+                x = x.cuda(non_blocking=True)
+            if moments is None:
+                dev = x.device
+                moments = torch.zeros((tr.channels, 2), dtype=torch.float64, device=dev)
+            tr.feat_moments, tr.store, tr.fused_norm = moments, False, None
+            _, welford_dict = tr(x)
+            if isinstance(tr, Packets):
+                tr.block_norm_dict = welford_dict             # reference :439
+                frames = x.shape[0] if x.dim() > 1 else 1
+                count += frames * wpt_out_len(x.shape[-1], len(tr.wavelet.dec_lo), tr.max_lev) * (1 << tr.max_lev)
+            else:
+                frames = x.shape[0] if x.dim() > 1 else 1
+                t, bins = stft_out_shape(x.shape[-1], tr.n_fft, tr.hop_length)
+                count += frames * t * bins
+    finally:
+        tr.feat_moments, tr.store, tr.fused_norm = saved
+    if moments is None:
+        raise ValueError("calc_normalization: no batches")
+    mean = moments[:, 0] / count
+    std = torch.sqrt(torch.clamp(moments[:, 1] / count - mean * mean, min=0))
+    return welford_dict, mean.float(), std.float()
+
+
+def fuse_normalize(transforms: torch.nn.Sequential, normalize: torch.nn.Sequential):
+    """Fold ``normalize`` (the reference's separate Normalize module, :380-382) into the transform kernel's
+    epilogue: returns ``(transforms, identity)`` so callers keep the two-step call pattern
+    (train_classifier.py:965-967) while the features touch HBM once."""
+    norm = normalize[0]
+    transforms[0].fused_norm = (norm.mean, norm.std)
+    return transforms, torch.nn.Sequential(torch.nn.Identity())
+
+
 def normalization_stats(feature_batches) -> tuple[torch.Tensor, torch.Tensor]:
-    """Per-channel mean / std over an iterable of feature tensors ``[B, C, P, T]`` -- the quantity
-    ``calc_normalization`` (reference wavelet_math.py:387-452) obtains with a WelfordEstimator."""
+    """Per-channel mean / std over an iterable of feature tensors ``[B, C, P, T]`` that already exist
+    (``calc_normalization`` is the fused route from audio)."""
     count, s, ss = 0, None, None
     for f in feature_batches:
         c = f.shape[1]

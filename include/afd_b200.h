@@ -72,6 +72,31 @@ int afd_wpt_forward(const float* x, int64_t B, int64_t N, int64_t x_row_stride,
                     float* out, int64_t* T_out, void* stream);
 
 /*
+ * Same transform with the rest of the reference's per-batch bookkeeping fused into the kernel's epilogue.
+ * Replaces, in addition to afd_wpt_forward: the per-node WelfordEstimator updates and the block norm of
+ * wavelet_math.py:194-203 (data_loader.py:41-63), torchvision Normalize (wavelet_math.py:380-382) and the
+ * feature statistics pass of calc_normalization (wavelet_math.py:436-441).  Every pointer below is optional.
+ *
+ *   node_scale          device fp32 [P]: the coefficients of output column p (frequency / natural order as
+ *                       requested) are multiplied by node_scale[p] before the epilogue.  Block norm
+ *                       (node / max|node|, :202-203) passes 1 / max|c_p| from a previous node_stats launch.
+ *   norm_mean_std_host  HOST fp32 [C][2] = (mean, std) per channel: features leave as (v - mean) / std.
+ *   node_stats          device DOUBLE [3][P], accumulated: [0][p] += sum c, [1][p] += sum c^2,
+ *                       [2][p] = max([2][p], max|c|) over the B*T RAW coefficients of column p (before
+ *                       node_scale).  With the count B*T these give every WelfordEstimator's mean / M2.
+ *   feat_moments        device DOUBLE [C][2], accumulated: sum and sum of squares of the features of each channel
+ *                       BEFORE normalisation (what calc_normalization feeds its estimator).
+ *   out                 may be NULL when node_stats or feat_moments is given: statistics only, no feature
+ *                       tensor is written (the first pass of block norm, calc_normalization).
+ */
+int afd_wpt_forward_ex(const float* x, int64_t B, int64_t N, int64_t x_row_stride,
+                       const double* dec_lo_host, int F, int level, int order,
+                       float power, int log_scale, float log_offset, int sign_channel,
+                       const float* node_scale, const float* norm_mean_std_host,
+                       double* node_stats, double* feat_moments,
+                       float* out, int64_t* T_out, void* stream);
+
+/*
  * Same transform with HOST input and output buffers (pinned memory recommended): frames are streamed through
  * the device in chunks with H2D copy, kernel and D2H copy overlapped on separate streams.  Blocks until `out_host`
  * is complete.  This is the call a CPU-side user of the reference (numpy in, numpy out) would make.
@@ -92,6 +117,17 @@ int afd_wpt_forward_host(const float* x_host, int64_t B, int64_t N, int64_t x_ro
 int afd_stft_power(const float* x, int64_t B, int64_t N, int64_t x_row_stride,
                    int n_fft, int hop, float power, int log_scale, float log_offset,
                    float* out, void* stream);
+
+/*
+ * Same transform with torchvision Normalize (wavelet_math.py:380-382) and the feature statistics of
+ * calc_normalization (wavelet_math.py:436-441) fused into the epilogue; both pointers optional.
+ *   norm_mean_std_host  HOST fp32 [2] = (mean, std): features leave as (v - mean) / std.
+ *   feat_moments        device DOUBLE [2], accumulated: sum and sum of squares of the features BEFORE normalisation.
+ *   out                 may be NULL when feat_moments is given (statistics only).
+ */
+int afd_stft_power_ex(const float* x, int64_t B, int64_t N, int64_t x_row_stride,
+                      int n_fft, int hop, float power, int log_scale, float log_offset,
+                      const float* norm_mean_std_host, double* feat_moments, float* out, void* stream);
 
 /* frames = 1 + (N + 2*(n_fft/2) - n_fft) / hop  (torch.stft, center=True), bins = n_fft / 2 + 1 */
 int afd_stft_out_shape(int64_t N, int n_fft, int hop, int64_t* frames, int64_t* bins);

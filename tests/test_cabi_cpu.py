@@ -58,6 +58,9 @@ def test_validation_errors_carry_a_message():
     assert lib.afd_wpt_forward(None, 1, 22050, 22050, None, 10, 8, 0, 2.0, 1, 1e-12, 0, None, None, None) == -1
     assert lib.afd_stft_power(None, 1, 22050, 22050, 511, 220, 2.0, 1, 1e-12, None, None) == -1
     assert lib.afd_haar_fingerprint_accum(None, 1, 22050, 22050, 14, None, None, None) == -1
+    assert lib.afd_wpt_forward_ex(None, 1, 22050, 22050, None, 10, 8, 0, 2.0, 1, 1e-12, 0, None, None, None, None, None,
+                                  None, None) == -1
+    assert lib.afd_stft_power_ex(None, 1, 22050, 22050, 511, 220, 2.0, 1, 1e-12, None, None, None, None) == -1
     with pytest.raises(_lib.AfdError) as info:
         _lib.check("afd_wpt_out_len", lib.afd_wpt_out_len(22050, 7, 8, ctypes.byref(out)))
     assert info.value.code == -1
