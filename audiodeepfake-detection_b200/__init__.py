@@ -20,7 +20,8 @@ from .wavelet_math import (  # noqa: F401
     wpt_out_len,
     stft_out_shape,
 )
-from . import fingerprint  # noqa: F401
+from . import fingerprint, framing  # noqa: F401
+from .framing import cut_frames, utterance_features  # noqa: F401
 from .fingerprint import FingerprintAccumulator, compute_fingerprint_wpt, haar_fingerprint  # noqa: F401
 
 __version__ = "0.1.0"

@@ -236,7 +236,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline leg")
-    ap.add_argument("--e2e-chunk", type=int, default=512, help="frames per pipelined chunk of the host-buffer call")
+    ap.add_argument("--e2e-chunk", type=int, default=256, help="frames per pipelined chunk of the host-buffer call")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -265,7 +265,19 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to stdout on first use: route fd 1 to stderr until the communicator exists,
+        # so that stdout carries exactly the one JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     lib = _lib.load()
 
     B = args.batch
@@ -309,9 +321,12 @@ def main():
     barrier()
     ms_local = e0.elapsed_time(e1)
     t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+    per_rank = [t.clone() for _ in range(world)]
     if world > 1:
+        dist.all_gather(per_rank, t)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
+    ms_per_rank = [float(v.item()) / args.steps for v in per_rank]
     ms_step = ms_total / args.steps
     value = B * world * args.steps / (ms_total * 1e-3)
     del out
@@ -399,6 +414,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg["config"],
         "clocks": clk.summary(), "gpu_launches": args.steps * launches_per_step, "roofline": roofline,
+        "ms_per_step_by_rank": ms_per_rank,
     }
     if e2e is not None:
         line["e2e"] = e2e

@@ -119,3 +119,32 @@ def test_strided_rows_and_odd_alignment(cuda_device):
     assert torch.equal(afd.wavelet_packet_features(view, w, 8), afd.wavelet_packet_features(view.contiguous(), w, 8))
     assert torch.equal(afd.stft_power_features(view), afd.stft_power_features(view.contiguous()))
     assert torch.allclose(afd.haar_fingerprint(view), afd.haar_fingerprint(view.contiguous()), rtol=1e-12)
+
+
+def test_frame_cutter_is_a_view_and_matches_host_slicing(cuda_device):
+    """cut_frames reproduces the reference's window table (data_loader.py:178-182, 336-340) without a copy."""
+    wave = torch.randn(1, 22050 * 3 + 777, device=cuda_device) * 0.1
+    frames = afd.cut_frames(wave, seconds=1, sample_rate=22050)
+    assert frames.shape == (3, 1, 22050) and frames.data_ptr() == wave.data_ptr()
+    tr = afd.Packets("sym5", 8, log_scale=True)
+    got, _ = afd.utterance_features(tr, wave)
+    for i in range(3):
+        want, _ = tr(wave[:, i * 22050:(i + 1) * 22050].clone().unsqueeze(0))
+        assert torch.equal(got[i:i + 1], want)
+    with pytest.raises(ValueError):
+        afd.cut_frames(wave[:, :1000])
+
+
+def test_training_step_consumes_features_on_device(cuda_device):
+    """BASELINE config 5 in miniature: fused features (no_grad) -> Normalize -> DCNN fwd/bwd -> Adam, loss falls."""
+    from audiodeepfake_detection_b200.train_step import TrainStep
+
+    torch.manual_seed(0)
+    tr, norm = afd.get_transforms(_args(), "none", cuda_device, False)
+    step = TrainStep(tr, norm, time_len=95, time_dim_add=1, device=cuda_device)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(16, 1, 22050, generator=g) * 0.1
+    x[8:] = x[8:] * torch.linspace(0.2, 1.0, 22050)        # two separable "classes"
+    y = torch.cat([torch.zeros(8), torch.ones(8)]).long()
+    losses = [float(step(x, y)) for _ in range(12)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
