@@ -22,6 +22,12 @@ from .wavelet_math import (  # noqa: F401
 )
 from . import fingerprint, framing  # noqa: F401
 from .framing import cut_frames, utterance_features  # noqa: F401
-from .fingerprint import FingerprintAccumulator, compute_fingerprint_wpt, haar_fingerprint  # noqa: F401
+from .fingerprint import (  # noqa: F401
+    FingerprintAccumulator,
+    SpectrumFingerprintAccumulator,
+    compute_fingerprint_rfft,
+    compute_fingerprint_wpt,
+    haar_fingerprint,
+)
 
 __version__ = "0.1.0"

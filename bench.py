@@ -45,6 +45,7 @@ WORKLOADS = {
     "sym5": ("packets", "sym5", 8, "configs[0] transform (level-8 sym5) at batch 4096"),
     "stft": ("stft", None, 0, "configs[2]: STFT power spectrogram 511/220, batch 4096"),
     "haar": ("haar", "haar", 14, "configs[3]: Haar level-14 mean|c| fingerprint, 4096 clips per step"),
+    "rfft": ("rfft", None, 0, "mean-spectrum fingerprint (fingerprints.py:37-62): clip-sum pass, 4096 clips per step"),
 }
 
 
@@ -83,6 +84,8 @@ def algorithmic_work(kind, wavelet, level, sign_channel=False):
             n = (n + 1) // 2
             coeffs += (1 << l) * n
         return 2.0 * 2 * coeffs, N_SAMPLES * 4
+    if kind == "rfft":
+        return float(N_SAMPLES), N_SAMPLES * 4          # one add per sample; the clips are read once
     raise ValueError(kind)
 
 
@@ -292,6 +295,12 @@ def main():
     elif kind == "stft":
         mod = afd.STFTLayer(n_fft=511, hop_length=220, log_scale=True, power=2.0)
         step = lambda: mod(x)[0]                                                    # noqa: E731
+    elif kind == "rfft":
+        acc = afd.SpectrumFingerprintAccumulator(N_SAMPLES, dev)
+        launches_per_step = 2
+        args.no_e2e = True          # no host-buffer entry point for this pass
+        args.no_cpu_baseline = True
+        step = lambda: acc.update(x)                                                # noqa: E731
     else:
         acc = afd.FingerprintAccumulator(level, dev)
         launches_per_step = 2

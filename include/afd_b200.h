@@ -151,6 +151,25 @@ int afd_haar_fingerprint_host(const float* x_host, int64_t B, int64_t N, int64_t
                               double* sums_host, int64_t* count_host, int device, int64_t chunk_frames);
 
 /*
+ * Mean-spectrum ("rFFT") fingerprint, part 1: per-sample sums over clips.
+ * Replaces: np.fft.rfft(clip_array) -> np.fft.irfft -> the sum part of np.mean(..., 0)
+ *           (scripts/freq_visual/fingerprints.py:51-59).  rfft -> irfft over all bins is the identity and the mean
+ *           is linear, so only the column sums of the clips are needed: one coalesced pass, nothing written.
+ *   sums   device DOUBLE [N]; sums[n] += sum over the B clips of x[b][n]
+ *   count  optional device int64 scalar; += B   (mean clip = sums / count, also after an all-reduce of both)
+ */
+int afd_clip_sum_accum(const float* x, int64_t B, int64_t N, int64_t x_row_stride,
+                       double* sums, int64_t* count, void* stream);
+
+/*
+ * Mean-spectrum fingerprint, part 2: mag[k] = | sum_n scale * x[n] * exp(-2 pi i k n / N) |, k = 0 .. N/2.
+ * Replaces: np.abs(np.fft.rfft(masked_time_mean))  (fingerprints.py:60); x = the clip sums, scale = 1 / count.
+ * One direct real DFT in double precision with exact phase reduction (any N up to 2^24; N = 22050 has no
+ * power-of-two path and the transform runs once per fingerprint).  x: device DOUBLE [N]; mag: device DOUBLE [N/2+1].
+ */
+int afd_rdft_magnitude(const double* x, int64_t N, double scale, double* mag, void* stream);
+
+/*
  * Diagnostic: the paraunitary lattice (plane rotations + unit delays) the wavelet-packet kernel evaluates instead
  * of the direct-form filter pair when `usable` is 1 -- half the multiplies per coefficient pair.  tan_theta
  * receives F/2 stage tangents (stage 0 first), scale the product of the stage cosines, residual the largest

@@ -126,3 +126,18 @@ def haar_fingerprint_sums(clips, level=14, dtype=np.float32):
     wp = packet_coefficients(x, DEC_LO["haar"], level, "freq", dtype)  # [B, T, P]
     sums = np.abs(wp).astype(np.float64).sum(axis=(0, 1))
     return sums, wp.shape[0] * wp.shape[1]
+
+
+def rfft_fingerprint(clips):
+    """Mean-spectrum fingerprint exactly as the reference chains it (fingerprints.py:51-62, use = all bins):
+    rfft of every clip -> concatenate with an empty zero block -> irfft -> mean over clips -> |rfft|.
+    ``clips``: [n, 1, N] (the reference's clip_array); returns (freqs, mean_abs_fft) with N // 2 + 1 entries."""
+    clip_array = np.asarray(clips)
+    freq_clips = np.fft.rfft(clip_array.astype(np.float64), axis=-1)
+    use = freq_clips.shape[-1]
+    zeros = np.zeros_like(freq_clips)[:, :, :-use]
+    masked_freq = np.concatenate([zeros, freq_clips[:, :, -use:]], -1)
+    masked_time_mean = np.mean(np.fft.irfft(masked_freq), 0)[0]
+    mean_abs_fft = np.abs(np.fft.rfft(masked_time_mean)[-use:])
+    freqs = np.fft.rfftfreq(masked_time_mean.shape[-1], 1.0 / 22050)[-use:]
+    return freqs, mean_abs_fft

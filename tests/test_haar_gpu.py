@@ -54,3 +54,30 @@ def test_energy_preservation_full_batch(cuda_device):
     g = torch.Generator(device="cuda").manual_seed(6)
     y = torch.randn(4096, 22050, device=cuda_device, generator=g)
     assert torch.allclose(afd.haar_fingerprint(3.0 * y, 14), 3.0 * afd.haar_fingerprint(y, 14), rtol=1e-5)
+
+
+@pytest.mark.parametrize("B,N", [(37, 22050), (3, 2206), (1, 22050)])
+def test_rfft_fingerprint_matches_reference_chain(B, N):
+    """Mean-spectrum fingerprint (reference fingerprints.py:37-62): column sums on the GPU + one fp64 DFT."""
+    from oracle import wpt_oracle
+
+    rng = np.random.default_rng(B)
+    clips = (rng.standard_normal((B, 1, N)) * 0.1 + 0.01).astype(np.float32)
+    _, want = wpt_oracle.rfft_fingerprint(clips)
+    acc = afd.SpectrumFingerprintAccumulator(N, "cuda")
+    xt = torch.from_numpy(clips).cuda()
+    half = B // 2
+    if half:
+        acc.update(xt[:half])                  # streaming: two updates equal one
+    acc.update(xt[half:])
+    got = acc.magnitude().cpu().numpy()
+    assert got.shape == want.shape and int(acc.count.item()) == B
+    assert np.max(np.abs(got - want)) < 1e-9 * np.max(want) + 1e-12
+
+
+def test_compute_fingerprint_rfft_surface():
+    clips = torch.randn(5, 1, 22050 + 100) * 0.1
+    freqs, fp = afd.compute_fingerprint_rfft(clips, seconds=1, amount=4)
+    assert freqs.shape == fp.shape == (11026,) and float(freqs[-1]) == 11025.0 and fp.is_cuda
+    with pytest.raises(ValueError):
+        afd.SpectrumFingerprintAccumulator(22051)
