@@ -162,15 +162,19 @@ __device__ __forceinline__ void pfa_gemm(uint32_t a_addr, const float4* __restri
     }
 }
 
+// MODE 0: power 2 + log (the reference's configuration), 1: power 2, linear, 2: any power / log flag (runtime)
+template <int MODE>
 __device__ __forceinline__ float pfa_finish(float re, float im, const PfaParams& p) {
     float v = fmaf(re, re, im * im);
+    if (MODE == 0) return ln_approx(v + p.log_offset);
+    if (MODE == 1) return v;
     if (!p.square) v = powf(sqrtf(v), p.power);
     if (p.log_scale) v = __logf(v + p.log_offset);
     return v;
 }
 
 // tables (device, float): [0, kPfaBFloats) B fragments; then kPfaWFloats window values.
-template <bool EXT>
+template <bool EXT, int MODE>
 __global__ void __launch_bounds__(kPfaThreads, 1)
 stft_pfa511_kernel(const float* __restrict__ x, long long x_row_stride, float* __restrict__ out,
                    const float* __restrict__ tables, const __grid_constant__ PfaParams p) {
@@ -313,8 +317,8 @@ stft_pfa511_kernel(const float* __restrict__ x, long long x_row_stride, float* _
                     const float vre = acc[1][0][nt][c], vim = acc[1][1][nt][c];      // zero for j = 0
                     const uint32_t bp = bins[nt] >> (8 * (c & 1));
                     float* orow = s_out + row * kPfaOutStride;
-                    orow[bp & 255u] = pfa_finish(ure - vim, uim + vre, p);
-                    if (wj != 0 && k2 != 0) orow[(bp >> 16) & 255u] = pfa_finish(ure + vim, vre - uim, p);
+                    orow[bp & 255u] = pfa_finish<MODE>(ure - vim, uim + vre, p);
+                    if (wj != 0 && k2 != 0) orow[(bp >> 16) & 255u] = pfa_finish<MODE>(ure + vim, vre - uim, p);
                 }
             }
         }
@@ -428,11 +432,16 @@ int stft_pfa511_launch(const float* x, int64_t B, int64_t N, int64_t x_row_strid
     const int smem = static_cast<int>(sizeof(float)) *
                      (kPfaBFloats + kPfaWFloats + kPfaGroups * (kPfaAFloats + kPfaRawFloats));
     const bool ext = ex.normalize || ex.moments || !out;
-    auto kern = ext ? stft_pfa511_kernel<true> : stft_pfa511_kernel<false>;
-    static thread_local bool configured[2][16] = {{false}, {false}};
-    if (dev >= 16 || !configured[ext][dev]) {
+    const int mode = p.square ? (p.log_scale ? 0 : 1) : 2;
+    using Kern = void (*)(const float*, long long, float*, const float*, const PfaParams);
+    static const Kern kerns[2][3] = {
+        {stft_pfa511_kernel<false, 0>, stft_pfa511_kernel<false, 1>, stft_pfa511_kernel<false, 2>},
+        {stft_pfa511_kernel<true, 0>, stft_pfa511_kernel<true, 1>, stft_pfa511_kernel<true, 2>}};
+    Kern kern = kerns[ext][mode];
+    static thread_local bool configured[2][3][16] = {};
+    if (dev >= 16 || !configured[ext][mode][dev]) {
         AFD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        if (dev < 16) configured[ext][dev] = true;
+        if (dev < 16) configured[ext][mode][dev] = true;
     }
     int sms = kNumSmsFallback;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
