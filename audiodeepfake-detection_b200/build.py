@@ -34,17 +34,22 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu under csrc/ into one shared library (objects built in parallel)."""
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out_path: str = LIB_PATH,
+          ) -> str:
+    """Compile every .cu under csrc/ into one shared library (objects built in parallel).
+
+    ``extra_flags`` / ``out_path`` build tuning variants next to the product library for same-box A/B runs
+    (tools/ab_bench.py), e.g. ``build(True, extra_flags=["-DAFD_WPT_FFMA2=0"], out_path=".../libafd_b200_prev.so")``."""
+    if not force and not _stale() and out_path == LIB_PATH:
         return LIB_PATH
     nvcc = _nvcc()
-    obj_dir = os.path.join(PKG_DIR, "build")
+    variant = out_path != LIB_PATH
+    obj_dir = os.path.join(PKG_DIR, "build", "variant") if variant else os.path.join(PKG_DIR, "build")
     os.makedirs(obj_dir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -56,8 +61,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(obj)
-    subprocess.check_call([nvcc, "-shared", "-o", LIB_PATH, *objs, "-lcudart"])
-    return LIB_PATH
+    subprocess.check_call([nvcc, "-shared", "-o", out_path, *objs, "-lcudart"])
+    return out_path
 
 
 if __name__ == "__main__":

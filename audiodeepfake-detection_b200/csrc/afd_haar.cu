@@ -170,26 +170,54 @@ struct HaarFastPlan {
     float final_scale;          // (1/sqrt 2)^L
 };
 
-template <int SPAN>
-__device__ __forceinline__ void haar_stage(float (&v)[32]) {
+// Butterfly stages.  From span 2 on, two adjacent elements ride in one 64-bit operand and the sum / difference are
+// packed fp32x2 adds (add.rn.f32x2 / sub.rn.f32x2 -> FADD2 on sm_100): half the issue slots of the scalar form.
+// AFD_HAAR_FADD2=0 builds the scalar butterflies (A/B measurements).
+#ifndef AFD_HAAR_FADD2
+#define AFD_HAAR_FADD2 1
+#endif
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+template <int SPAN, int LEN>
+__device__ __forceinline__ void haar_stage_n(float (&v)[LEN]) {
+    if constexpr (SPAN >= 2 && AFD_HAAR_FADD2 != 0) {
 #pragma unroll
-    for (int p = 0; p < 32; ++p)
-        if ((p & SPAN) == 0) {
-            const float a = v[p], b = v[p + SPAN];
-            v[p] = a + b;
-            v[p + SPAN] = a - b;
-        }
+        for (int p = 0; p < LEN; p += 2)
+            if ((p & SPAN) == 0) {
+                const u64 a = pk2(v[p], v[p + 1]), b = pk2(v[p + SPAN], v[p + SPAN + 1]);
+                upk2(add2(a, b), v[p], v[p + 1]);
+                upk2(sub2(a, b), v[p + SPAN], v[p + SPAN + 1]);
+            }
+    } else {
+#pragma unroll
+        for (int p = 0; p < LEN; ++p)
+            if ((p & SPAN) == 0) {
+                const float a = v[p], b = v[p + SPAN];
+                v[p] = a + b;
+                v[p + SPAN] = a - b;
+            }
+    }
 }
 template <int SPAN>
-__device__ __forceinline__ void haar_stage16(float (&v)[16]) {
-#pragma unroll
-    for (int p = 0; p < 16; ++p)
-        if ((p & SPAN) == 0) {
-            const float a = v[p], b = v[p + SPAN];
-            v[p] = a + b;
-            v[p + SPAN] = a - b;
-        }
-}
+__device__ __forceinline__ void haar_stage(float (&v)[32]) { haar_stage_n<SPAN, 32>(v); }
+template <int SPAN>
+__device__ __forceinline__ void haar_stage16(float (&v)[16]) { haar_stage_n<SPAN, 16>(v); }
 
 template <int K>   // K = L - 10 levels in the last pass
 __global__ void __launch_bounds__(kFastThreads, 2)

@@ -212,6 +212,110 @@ __device__ __forceinline__ void lattice2(float (&w)[WLEN], const Coefs<F>& cf, f
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Packed fp32x2 arithmetic (sm_100: fma.rn.f32x2 -> FFMA2).  One FFMA2 does two FMAs in ONE issue slot at the same
+// pipe FLOP rate as two FFMAs (tools/probes/ffma2.cu: 73.6 vs 72.6 TFLOP/s), and these kernels are issue-bound, so
+// every FFMA pair folded into an FFMA2 is a freed slot.  64-bit operands are even-aligned register pairs: the
+// mov.b64 packs / unpacks below cost nothing when the register allocator can place the halves adjacently.
+// AFD_WPT_FFMA2=0 builds the scalar forms (A/B measurements).  Measured on B200 (gpurun_out/ab_ffma2.log): sym5 (F = 10)
+// 2 % faster, coif4 (F = 24) 1.5 % slower (the kernel is latency / barrier bound, not issue bound, and the packed
+// long-filter forms hold more live registers), so the packed forms are used for F <= kPackedMaxF only.
+// ------------------------------------------------------------------------------------------------
+#ifndef AFD_WPT_FFMA2
+#define AFD_WPT_FFMA2 1
+#endif
+constexpr int kPackedMaxF = 16;
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// Direct form, one filter, packed over tap pairs: y[r] = sum_q (t[2q] w[e+1] + t[2q+1] w[e]), e = 2r + F-2 - 2q (even),
+// so (w[e], w[e+1]) is an aligned pair of the 128-bit window loads.  t2[q] = (t[2q+1], t[2q]).  F/2 FFMA2 + 1 FADD per output.
+template <int F, int R, int WLEN>
+__device__ __forceinline__ void fir1_packed(const float (&w)[WLEN], const u64 (&t2)[F / 2], float (&y)[R]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        u64 acc = fma2(pk2(w[2 * r + F - 2], w[2 * r + F - 1]), t2[0], pk2(0.f, 0.f));
+#pragma unroll
+        for (int q = 1; q < F / 2; ++q) {
+            const int e = 2 * r + F - 2 - 2 * q;
+            acc = fma2(pk2(w[e], w[e + 1]), t2[q], acc);
+        }
+        float a, b;
+        upk2(acc, a, b);
+        y[r] = a + b;
+    }
+}
+
+// Lattice with the middle stages packed: pair indices i and i + H (H = ceil(NP / 2)) share one 64-bit operand, so the
+// unit delay (index shift by one) applies to whole operands.  Stage 0 (reads the window registers as loaded) and the
+// last stage (its outputs go to paired 64-bit shared-memory stores of adjacent coefficients) stay scalar, which lets
+// the register allocator form the pairs without moves.  The first half computes indices below the stage number that
+// the scalar form skips: (J-2) * H packed rotations instead of sum (NP - m) scalar ones.
+template <int F, int R, int WLEN>
+__device__ __forceinline__ void lattice2_packed(const float (&w)[WLEN], const Coefs<F>& cf, float (&lo)[R], float (&hi)[R]) {
+    constexpr int J = F / 2;
+    constexpr int NP = R + J - 1;
+    constexpr int H = (NP + 1) / 2;
+    static_assert(J >= 3, "packed lattice needs at least one middle stage");
+    static_assert(2 * NP <= WLEN, "window too short");
+    u64 U[H], V[H];
+    {
+        const float t0 = cf.t[0];
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            const float a0 = w[2 * i + 1], b0 = w[2 * i];
+            float u1 = 0.f, v1 = 0.f;
+            if (i + H < NP) {
+                const float a1 = w[2 * (i + H) + 1], b1 = w[2 * (i + H)];
+                u1 = fmaf(t0, b1, a1);
+                v1 = fmaf(-t0, a1, b1);
+            }
+            U[i] = pk2(fmaf(t0, b0, a0), u1);
+            V[i] = pk2(fmaf(-t0, a0, b0), v1);
+        }
+    }
+#pragma unroll
+    for (int m = 1; m < J - 1; ++m) {
+        const float tm = cf.t[m];
+        const u64 tp = pk2(tm, tm), tn = pk2(-tm, -tm);
+        float vl, vh;
+        upk2(V[H - 1], vl, vh);
+        const u64 vm1 = pk2(0.f, vl);                  // (index -1: never used, index H-1)
+#pragma unroll
+        for (int i = H - 1; i >= 0; --i) {
+            const u64 vp = i > 0 ? V[i - 1] : vm1;
+            const u64 un = fma2(tp, vp, U[i]);
+            V[i] = fma2(tn, U[i], vp);
+            U[i] = un;
+        }
+    }
+    {
+        const float tl = cf.t[J - 1];
+        float u[2 * H], v[2 * H];
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            upk2(U[i], u[i], u[i + H]);
+            upk2(V[i], v[i], v[i + H]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = J - 1 + r;
+            lo[r] = fmaf(tl, v[i - 1], u[i]);
+            hi[r] = fmaf(-tl, u[i], v[i - 1]);
+        }
+    }
+}
+
 template <int F, int R>
 struct Win {
     static constexpr int W = 2 * R + F - 2;   // window length
@@ -235,7 +339,8 @@ __device__ __forceinline__ void filter_pair(const float* __restrict__ src, const
     using WN = Win<F, R>;
     float w[WN::WLEN];
     load_window<WN::NV>(src, w);
-    if constexpr (LAT) lattice2<F, R>(w, cf, lo, hi);
+    if constexpr (LAT && AFD_WPT_FFMA2 && F >= 6 && F <= kPackedMaxF) lattice2_packed<F, R>(w, cf, lo, hi);
+    else if constexpr (LAT) lattice2<F, R>(w, cf, lo, hi);
     else fir2<F, R>(w, cf, lo, hi);
 }
 
@@ -388,7 +493,7 @@ __device__ __forceinline__ void mid_level(const float* __restrict__ in, float* _
 // Sample 2*kb + 2 - F of the (reflect-extended) frame sits at buf[0].
 template <int F, int R>
 __device__ __forceinline__ void level1_chunk(const float* __restrict__ buf, float* __restrict__ node, int kb, int ke,
-                                             int n_out, const Split& sp, const float (&t)[F]) {
+                                             int n_out, const Split& sp, const float (&t)[F], const u64 (&t2)[F / 2]) {
     using WN = Win<F, R>;
     constexpr int padl = F - 2;
     const int items = (ke - kb + R - 1) / R;
@@ -399,7 +504,8 @@ __device__ __forceinline__ void level1_chunk(const float* __restrict__ buf, floa
         float w[WN::WLEN];
         load_window<WN::NV>(buf + 2 * i * R, w);
         float y[R];
-        fir1<F, R>(w, t, y);
+        if constexpr (AFD_WPT_FFMA2 != 0 && F <= kPackedMaxF) fir1_packed<F, R>(w, t2, y);
+        else fir1<F, R>(w, t, y);
         if (c >= sp.CL && c < sp.CIe) vec_store<R>(node + padl + k0, y);
         else edge_store<R>(node, y, k0, n_out, padl);
     }
@@ -577,6 +683,9 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
     float t1[F];
 #pragma unroll
     for (int m = 0; m < F; ++m) t1[m] = half ? cf.hi[m] : cf.lo[m];
+    u64 t1p[F / 2];                                        // (t[2q+1], t[2q]) for the packed direct form
+#pragma unroll
+    for (int q = 0; q < F / 2; ++q) t1p[q] = pk2(t1[2 * q + 1], t1[2 * q]);
     bool prefetched = false;
     bool first = true;
     ThreadStats ts;
@@ -601,7 +710,7 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
             if (j + 1 < plan.nch) issue_chunk<F>(xg, ((j + 1) & 1) ? buf1 : buf0, j + 1, plan);
             const int kb = j * plan.kc;
             const int ke = min(n1, kb + plan.kc);
-            level1_chunk<F, R1>((j & 1) ? buf1 : buf0, regA, kb, ke, n1, sp1, t1);
+            level1_chunk<F, R1>((j & 1) ? buf1 : buf0, regA, kb, ke, n1, sp1, t1, t1p);
         }
         __syncthreads();
         float* out_b = out + b * C * static_cast<long long>(T) * P;
