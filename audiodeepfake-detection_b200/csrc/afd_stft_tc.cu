@@ -1,0 +1,550 @@
+// STFT power spectrogram for n_fft = 511 = 7 * 73 on sm_100a, tcgen05 version: the prime-factor real DFT of
+// afd_stft_pfa.cu with the 73-point stage on the 5th-generation tensor cores (tcgen05.mma kind::tf32, operands in
+// shared memory, accumulators in tensor memory) and a warp-specialised persistent CTA around it.
+//
+// Replaces torchaudio.transforms.Spectrogram(511, hop, power) -> torch.stft(center=True, pad_mode="reflect",
+// window=hann_window(511) [periodic], onesided=True) -> abs().pow(power) and the optional log(spec + 1e-12)
+// of the reference (wavelet_math.py:47,63-66).  Algorithm (fold, DFT-7, DFT-73 as two real GEMMs against cos / -sin,
+// combine): see the header of afd_stft_pfa.cu; the arithmetic outside the GEMM is the same.
+//
+// Mapping.  A unit = 16 consecutive STFT frames of one signal.  Its seven real sequences (u0, u1, v1, u2, v2, u3, v3)
+// are the rows of ONE 128-row MMA tile: row = 32 j + 16 h + f  (j = 0..3, h = 0: u_j / 1: v_j, f = frame; rows
+// 16..31 stay zero), columns = [P (m = 0..36, padded to 40) | Q (m = 1..36 at 41..76, padded to 80)].
+//     D[:, 0:48]  = A[:, 0:40]  x C      (Re part, C[m][k2] =  cos(2 pi m k2 / 73), N padded 37 -> 48)
+//     D[:, 48:96] = A[:, 40:80] x S      (Im part, S[m][k2] = -sin(2 pi m k2 / 73))
+// Each product is 3xTF32 error compensated: A and the tables are split into a TF32-exact high part and an fp32 remainder
+// (two shared-memory copies each) and D accumulates lo*hi + hi*lo + hi*hi in fp32 -> fp32-level accuracy.  30
+// tcgen05.mma (M = 128, N = 48, K = 8) per unit, issued by one thread.
+// Shared-memory operand layout: the canonical K-major no-swizzle layout (8-row x 16-byte core matrices); consecutive
+// 16-byte K chunks of the A tile are 144 bytes apart so that the 37 lanes that write one row segment hit distinct banks.
+//
+// Roles of the 16 warps of the one CTA per SM (each role walks the same unit sequence):
+//     warps 8..14  producers : stage the unit's samples (cp.async, next unit prefetched), window, fold, two 7-point real
+//                              DFTs per (frame, m), hi / lo split, store into the A tiles, arrive on `a_full`
+//     warp 15      MMA issuer: waits `a_full` (+ `d_empty` of the accumulator buffer), issues the 30 MMAs, commits to
+//                              `a_free` (producers may overwrite A) and `d_full` (accumulators ready)
+//     warps 0..7   epilogue  : warp w reads TMEM lanes 32 (w % 4) .. +31 (= j), half w / 4 of the k2 range;
+//                              tcgen05.ld, partner exchange (u <-> v sit 16 lanes apart), |Z|^2, log -> 16 x 256 tile in
+//                              shared memory (double buffered) -> 128-bit coalesced streaming stores.
+// Accumulators are double buffered in TMEM (2 x 96 of 256 allocated columns), so unit n's epilogue overlaps unit
+// n+1's producer phase; the tensor phase itself is ~0.5 us per unit.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "afd_common.cuh"
+
+namespace afd {
+
+namespace tc {
+
+constexpr int kN = 511;
+constexpr int kRows = 16;                     // STFT frames per unit
+constexpr int kEpiWarps = 8, kPreWarps = 10;
+constexpr int kEpiThreads = kEpiWarps * 32;   // 256
+constexpr int kPreThreads = kPreWarps * 32;   // 320
+constexpr int kThreads = kEpiThreads + kPreThreads + 32;   // + MMA warp = 608
+constexpr int kPreSubs = 8;                   // producer thread = (m, sub): rows sub and sub + 8
+
+// A tile (bytes): 128 rows x 80 columns of fp32, K-major core matrices
+constexpr int kALbo = 144;                    // distance of consecutive 16-byte K chunks
+constexpr int kASbo = 20 * kALbo;             // distance of consecutive 8-row groups (2880)
+constexpr int kATile = 16 * kASbo;            // 46080
+// B tiles (bytes): 48 rows (k2) x 40 columns (m)
+constexpr int kBLbo = 128;
+constexpr int kBSbo = 10 * kBLbo;             // 1280
+constexpr int kBTile = 6 * kBSbo;             // 7680
+constexpr int kRawFloats = 4160;              // >= 15 * hop + 511 + 6  (hop <= 242)
+constexpr int kMaxHop = (kRawFloats - kN - 6) / (kRows - 1);
+constexpr int kOutStride = 260;               // floats per row of the output tile
+constexpr int kOutFloats = kRows * kOutStride;
+constexpr int kWFloats = 2 * 37 * 8;
+
+// shared-memory map (bytes)
+constexpr int kOffAHi = 0;
+constexpr int kOffALo = kOffAHi + kATile;
+constexpr int kOffB = kOffALo + kATile;                      // C hi, C lo, S hi, S lo
+constexpr int kOffRaw = kOffB + 4 * kBTile;                  // two staging buffers
+constexpr int kOffOut = kOffRaw + 2 * kRawFloats * 4;        // two output tiles
+constexpr int kOffW = kOffOut + 2 * kOutFloats * 4;
+constexpr int kOffBar = kOffW + kWFloats * 4;                // mbarriers + TMEM base address
+constexpr int kSmemBytes = kOffBar + 128;
+constexpr int kTableFloats = 4 * kBTile / 4 + kWFloats;      // device table: B tiles (byte-exact smem image) + window
+
+constexpr int kTmemCols = 256;
+constexpr int kDStride = 128;                 // TMEM columns between the two accumulator buffers
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((48u >> 3) << 17) | ((128u >> 4) << 24);
+
+struct Params {
+    int hop, frames, N, pad, units_per_row, vec_ok;
+    long long total_units;
+    float power, log_offset;
+    int log_scale, square;
+    int normalize, store;
+    float nmean, nrstd;
+    double* moments;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// ---- mbarrier
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1u << 26)) __trap();       // a lost arrival must not hang the GPU
+    }
+}
+__device__ __forceinline__ void named_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// ---- tcgen05
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no swizzle, version 1 (sm_100) shared-memory matrix descriptor
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return static_cast<uint64_t>((addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16) |
+           (static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+// 7-point DFT of a real sequence p[0..6]: r[0] = X0, (r[2j-1], r[2j]) = (Re Xj, Im Xj), j = 1..3.
+__device__ __forceinline__ void dft7_real(const float (&p)[7], float (&r)[7]) {
+    constexpr float c1 = 0.62348980185873353f, c2 = -0.22252093395631440f, c3 = -0.90096886790241913f;
+    constexpr float s1 = 0.78183148246802981f, s2 = 0.97492791218182361f, s3 = 0.43388373911755812f;
+    const float a1 = p[1] + p[6], a2 = p[2] + p[5], a3 = p[3] + p[4];
+    const float b1 = p[1] - p[6], b2 = p[2] - p[5], b3 = p[3] - p[4];
+    r[0] = (p[0] + a1) + (a2 + a3);
+    r[1] = fmaf(c3, a3, fmaf(c2, a2, fmaf(c1, a1, p[0])));
+    r[3] = fmaf(c1, a3, fmaf(c3, a2, fmaf(c2, a1, p[0])));
+    r[5] = fmaf(c2, a3, fmaf(c1, a2, fmaf(c3, a1, p[0])));
+    r[2] = -fmaf(s3, b3, fmaf(s2, b2, s1 * b1));
+    r[4] = -fmaf(-s1, b3, fmaf(-s3, b2, s2 * b1));
+    r[6] = -fmaf(s2, b3, fmaf(-s1, b2, s3 * b1));
+}
+
+// Stage the samples of unit (b, t0) into `raw`: raw[aoff + i] = x~[t0*hop - pad + i], x~ = reflect extension.
+__device__ __forceinline__ void stage(const float* __restrict__ xrow, long long g0, float* __restrict__ raw, int t0,
+                                      int valid, const Params& p, int pt) {
+    const int S0 = t0 * p.hop - p.pad;                       // first sample of the unit (may be negative)
+    const int len = (valid - 1) * p.hop + kN;
+    const int aoff = static_cast<int>((g0 + S0) & 3);        // element misalignment of x~[S0]
+    const int nq = (aoff + len + 3) >> 2;
+    const int N = p.N;
+    for (int q = pt; q < nq; q += kPreThreads) {
+        const int s0 = S0 - aoff + 4 * q;
+        float* dst = raw + 4 * q;
+        if (p.vec_ok && s0 >= 0 && s0 + 3 < N) {
+            cp_async_16(dst, xrow + s0);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                int s = s0 + e;
+                s = s < 0 ? -s : s;
+                s = s >= N ? 2 * (N - 1) - s : s;
+                s = max(0, min(s, N - 1));
+                cp_async_4(dst + e, xrow + s);
+            }
+        }
+    }
+    cp_async_commit();
+}
+
+// MODE 0: power 2 + log (the reference's configuration), 1: power 2, linear, 2: any power / log flag (runtime)
+template <int MODE>
+__device__ __forceinline__ float finish(float re, float im, const Params& p) {
+    float v = fmaf(re, re, im * im);
+    if (MODE == 0) return ln_approx(v + p.log_offset);
+    if (MODE == 1) return v;
+    if (!p.square) v = powf(sqrtf(v), p.power);
+    if (p.log_scale) v = __logf(v + p.log_offset);
+    return v;
+}
+
+// Epilogue of one unit for the warps of k2 half KH: accumulator columns -> output tile.
+template <int MODE, int KH>
+__device__ __forceinline__ void combine(uint32_t taddr, uint32_t bar_d_empty, float* __restrict__ orow, const uint32_t (&binpk)[5],
+                                        bool lane_live, int j, int h, const Params& p) {
+    constexpr int kLo = KH ? 19 : 0, kHi = KH ? 36 : 18;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int col0 = (KH ? 16 : 0) + 8 * c;
+        float re[8], im[8];
+        tc_ld8(taddr + col0, re);
+        tc_ld8(taddr + 48 + col0, im);
+        tc_ld_wait();
+        if (c == 2) {                          // every accumulator of the unit is in registers: release the buffer
+            tc_fence_before();
+            mbar_arrive(bar_d_empty);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int k2 = col0 + i;
+            if (k2 < kLo || k2 > kHi) continue;
+            const float pre = __shfl_xor_sync(0xffffffffu, re[i], 16);
+            const float pim = __shfl_xor_sync(0xffffffffu, im[i], 16);
+            const float val = finish<MODE>(re[i] - pim, im[i] + pre, p);
+            const int idx = k2 - kLo;
+            const uint32_t bin = (binpk[idx >> 2] >> (8 * (idx & 3))) & 255u;
+            const bool live = lane_live && !(h == 1 && k2 == 0);
+            if (live) orow[bin] = val;
+        }
+    }
+    (void)j;
+}
+
+template <bool EXT, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __restrict__ out,
+                  const float* __restrict__ tables, const __grid_constant__ Params p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    float* const s_w = reinterpret_cast<float*>(smem + kOffW);
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t bar_a_full = s_base + kOffBar, bar_a_free = bar_a_full + 8;
+    const uint32_t bar_d_full = bar_a_full + 16, bar_d_empty = bar_a_full + 32;      // two each
+    uint32_t* const s_tmem = reinterpret_cast<uint32_t*>(smem + kOffBar + 64);
+
+    // ---- one-time setup: tables -> shared memory, A tiles zeroed, barriers, tensor memory
+    {
+        const float4* src = reinterpret_cast<const float4*>(tables);
+        float4* dstB = reinterpret_cast<float4*>(smem + kOffB);
+        for (int i = tid; i < 4 * kBTile / 16; i += kThreads) dstB[i] = __ldg(src + i);
+        for (int i = tid; i < kWFloats; i += kThreads) s_w[i] = __ldg(tables + kBTile + i);  // window follows the B tiles
+        float4* a = reinterpret_cast<float4*>(smem + kOffAHi);
+        for (int i = tid; i < 2 * kATile / 16; i += kThreads) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4* o = reinterpret_cast<float4*>(smem + kOffRaw);
+        for (int i = tid; i < (2 * kRawFloats + 2 * kOutFloats) / 4; i += kThreads) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (tid == 0) {
+        mbar_init(bar_a_full, kPreThreads);
+        mbar_init(bar_a_free, 1);
+        mbar_init(bar_d_full, 1);
+        mbar_init(bar_d_full + 8, 1);
+        mbar_init(bar_d_empty, kEpiThreads);
+        mbar_init(bar_d_empty + 8, kEpiThreads);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kThreads / 32 - 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes of the tables / zeros -> async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    const long long first_unit = blockIdx.x;
+    const long long ustride = gridDim.x;
+
+    if (warp < kEpiWarps) {
+        // ============================================================ epilogue warps
+        const int j = warp & 3, kh = warp >> 2;
+        const int h = lane >> 4, f = lane & 15;
+        const bool lane_live = !(h == 1 && j == 0);
+        uint32_t binpk[5] = {0u, 0u, 0u, 0u, 0u};
+        {
+            const int lo = kh ? 19 : 0, hi = kh ? 36 : 18;
+            for (int k2 = lo; k2 <= hi; ++k2) {
+                int kk = (365 * j + 147 * (h ? 73 - k2 : k2)) % kN;
+                kk = kk > 255 ? kN - kk : kk;
+                const int idx = k2 - lo;
+                binpk[idx >> 2] |= static_cast<uint32_t>(kk & 255) << (8 * (idx & 3));
+            }
+        }
+        float mom_s = 0.f, mom_q = 0.f;
+        const float n_rs = (EXT && p.normalize) ? p.nrstd : 1.f, n_dm = (EXT && p.normalize) ? -p.nmean * p.nrstd : 0.f;
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(32 * j) << 16);
+        int it = 0;
+        for (long long unit = first_unit; unit < p.total_units; unit += ustride, ++it) {
+            const long long b = unit / p.units_per_row;
+            const int t0 = static_cast<int>(unit - b * p.units_per_row) * kRows;
+            const int valid = min(kRows, p.frames - t0);
+            const int buf = it & 1;
+            float* const s_out = reinterpret_cast<float*>(smem + kOffOut) + buf * kOutFloats;
+            mbar_wait(bar_d_full + 8 * buf, (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = lane_addr + buf * kDStride;
+            if (kh == 0) combine<MODE, 0>(taddr, bar_d_empty + 8 * buf, s_out + f * kOutStride, binpk, lane_live, j, h, p);
+            else combine<MODE, 1>(taddr, bar_d_empty + 8 * buf, s_out + f * kOutStride, binpk, lane_live, j, h, p);
+            named_bar(1, kEpiThreads);                           // the unit's tile is complete
+            float* og = out + (b * p.frames + t0) * 256LL;
+            for (int i = tid; i < valid * 64; i += kEpiThreads) {
+                const int row = i >> 6, c4 = (i & 63) * 4;
+                float4 v = *reinterpret_cast<const float4*>(s_out + row * kOutStride + c4);
+                if (EXT && p.moments) {
+                    mom_s += (v.x + v.y) + (v.z + v.w);
+                    mom_q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, mom_q))));
+                }
+                if (EXT && p.normalize) {
+                    v.x = fmaf(v.x, n_rs, n_dm); v.y = fmaf(v.y, n_rs, n_dm);
+                    v.z = fmaf(v.z, n_rs, n_dm); v.w = fmaf(v.w, n_rs, n_dm);
+                }
+                if (!EXT || p.store) st_cs4(reinterpret_cast<float4*>(og + row * 256 + c4), v);
+            }
+            // the other tile is rewritten only after every thread passed the next unit's barrier
+        }
+        if (EXT && p.moments) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mom_s += __shfl_xor_sync(0xffffffffu, mom_s, o);
+                mom_q += __shfl_xor_sync(0xffffffffu, mom_q, o);
+            }
+            if (lane == 0) {
+                atomicAdd(p.moments, static_cast<double>(mom_s));
+                atomicAdd(p.moments + 1, static_cast<double>(mom_q));
+            }
+        }
+    } else if (warp < kEpiWarps + kPreWarps) {
+        // ============================================================ producer warps
+        const int pt = tid - kEpiThreads;
+        const bool active = pt < 37 * kPreSubs;
+        const int pm = pt % 37;
+        const int psub = pt / 37;
+        int offA[7], offB[7];
+        float wA[7], wB[7];
+#pragma unroll
+        for (int n1 = 0; n1 < 7; ++n1) {
+            int a = 73 * n1 + 7 * pm;
+            a = a >= kN ? a - kN : a;
+            int bq = 73 * n1 - 7 * pm;
+            bq = bq < 0 ? bq + kN : bq;
+            offA[n1] = a;
+            offB[n1] = bq;
+            wA[n1] = s_w[pm * 8 + n1];
+            wB[n1] = s_w[(37 + pm) * 8 + n1];
+        }
+        unsigned char* const a_hi = smem + kOffAHi + (pm >> 2) * kALbo + (pm & 3) * 4;     // column m of the P block
+        constexpr int kQ = 10 * kALbo;                                                      // column 40 + m
+        float* const raw0 = reinterpret_cast<float*>(smem + kOffRaw);
+        if (first_unit < p.total_units) {
+            const long long b = first_unit / p.units_per_row;
+            const int t0 = static_cast<int>(first_unit - b * p.units_per_row) * kRows;
+            stage(x + b * x_row_stride, b * x_row_stride, raw0, t0, min(kRows, p.frames - t0), p, pt);
+        }
+        int it = 0;
+        for (long long unit = first_unit; unit < p.total_units; unit += ustride, ++it) {
+            const long long b = unit / p.units_per_row;
+            const int t0 = static_cast<int>(unit - b * p.units_per_row) * kRows;
+            const int valid = min(kRows, p.frames - t0);
+            const int aoff = static_cast<int>((b * x_row_stride + (t0 * p.hop - p.pad)) & 3);
+            const float* raw = raw0 + (it & 1) * kRawFloats;
+            cp_async_wait<0>();
+            named_bar(2, kPreThreads);                           // samples landed; the other buffer is no longer read
+            {
+                const long long nu = unit + ustride;
+                if (nu < p.total_units) {
+                    const long long nb = nu / p.units_per_row;
+                    const int nt0 = static_cast<int>(nu - nb * p.units_per_row) * kRows;
+                    stage(x + nb * x_row_stride, nb * x_row_stride, raw0 + ((it + 1) & 1) * kRawFloats, nt0,
+                          min(kRows, p.frames - nt0), p, pt);
+                }
+            }
+            // both rows of the thread are computed BEFORE the A tiles are claimed: this overlaps the previous unit's MMAs
+            float P[2][7], Q[2][7];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int r = psub + rr * kPreSubs;
+                if (active && r < valid) {
+                    const float* fr = raw + aoff + r * p.hop;
+                    float pp[7], qq[7];
+#pragma unroll
+                    for (int n1 = 0; n1 < 7; ++n1) {
+                        const float xa = fr[offA[n1]] * wA[n1];
+                        const float xb = fr[offB[n1]] * wB[n1];
+                        pp[n1] = xa + xb;
+                        qq[n1] = xa - xb;
+                    }
+                    dft7_real(pp, P[rr]);
+                    dft7_real(qq, Q[rr]);
+                }
+            }
+            if (it > 0) mbar_wait(bar_a_free, (it - 1) & 1);     // the previous unit's MMAs have read the A tiles
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int r = psub + rr * kPreSubs;
+                if (active && r < valid) {
+                    unsigned char* arow = a_hi + (r & 7) * 16 + (r >> 3) * kASbo;
+#pragma unroll
+                    for (int s = 0; s < 7; ++s) {
+                        const int row8 = s == 0 ? 0 : 4 * ((s + 1) >> 1) + 2 * ((s + 1) & 1);   // (32 j + 16 h) / 8
+                        {
+                            const float hi = __uint_as_float(__float_as_uint(P[rr][s]) & 0xffffe000u);
+                            *reinterpret_cast<float*>(arow + row8 * kASbo) = hi;
+                            *reinterpret_cast<float*>(arow + row8 * kASbo + kATile) = P[rr][s] - hi;
+                        }
+                        if (pm != 0) {
+                            const float hi = __uint_as_float(__float_as_uint(Q[rr][s]) & 0xffffe000u);
+                            *reinterpret_cast<float*>(arow + row8 * kASbo + kQ) = hi;
+                            *reinterpret_cast<float*>(arow + row8 * kASbo + kQ + kATile) = Q[rr][s] - hi;
+                        }
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(bar_a_full);
+        }
+        cp_async_wait<0>();
+    } else if (lane == 0) {
+        // ============================================================ MMA issuer (one thread)
+        const uint32_t a_hi = s_base + kOffAHi, a_lo = s_base + kOffALo;
+        const uint32_t b0 = s_base + kOffB;
+        int it = 0;
+        for (long long unit = first_unit; unit < p.total_units; unit += ustride, ++it) {
+            const int buf = it & 1;
+            mbar_wait(bar_a_full, it & 1);
+            if (it >= 2) mbar_wait(bar_d_empty + 8 * buf, ((it >> 1) - 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {               // 0: Re = P x C, 1: Im = Q x S
+                const uint32_t d = tmem_base + buf * kDStride + part * 48;
+                const uint32_t bh = b0 + (2 * part) * kBTile, bl = bh + kBTile;
+                const uint32_t ak = part * 10 * kALbo;
+#pragma unroll
+                for (int term = 0; term < 3; ++term) {           // small terms first: lo*hi, hi*lo, hi*hi
+                    const uint32_t at = (term == 0 ? a_lo : a_hi) + ak;
+                    const uint32_t bt = term == 1 ? bl : bh;
+#pragma unroll
+                    for (int ks = 0; ks < 5; ++ks)
+                        tc_mma_tf32(d, make_desc(at + 2 * ks * kALbo, kALbo, kASbo), make_desc(bt + 2 * ks * kBLbo, kBLbo, kBSbo),
+                                    (term | ks) != 0);
+                }
+            }
+            tc_commit(bar_a_free);
+            tc_commit(bar_d_full + 8 * buf);
+        }
+    }
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kThreads / 32 - 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static std::mutex g_mutex;
+static std::map<int, float*> g_tables;
+
+static float tf32_trunc(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u &= 0xffffe000u;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+static int get_tables(int dev, float** out) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    auto it = g_tables.find(dev);
+    if (it != g_tables.end()) { *out = it->second; return AFD_OK; }
+    std::vector<float> h(kTableFloats, 0.f);
+    auto bval = [](int part, int m, int k2) -> double {
+        if (m > 36 || k2 > 36) return 0.0;
+        const int ph = (m * k2) % 73;                                    // exact phase reduction
+        const double ang = 2.0 * M_PI * double(ph) / 73.0;
+        if (part == 0) return cos(ang);
+        return m == 0 ? 0.0 : -sin(ang);
+    };
+    for (int part = 0; part < 2; ++part)
+        for (int n = 0; n < 48; ++n)
+            for (int k = 0; k < 40; ++k) {
+                const double v = bval(part, k, n);
+                const float hi = tf32_trunc(static_cast<float>(v));
+                const float lo = static_cast<float>(v - static_cast<double>(hi));
+                const int byte = (n & 7) * 16 + (n >> 3) * kBSbo + (k >> 2) * kBLbo + (k & 3) * 4;
+                h[((2 * part) * kBTile + byte) / 4] = hi;
+                h[((2 * part + 1) * kBTile + byte) / 4] = lo;
+            }
+    auto hann = [](int n) { return 0.5 - 0.5 * cos(2.0 * M_PI * double(n) / double(kN)); };   // periodic Hann
+    float* w = h.data() + kBTile;                                         // 4 * kBTile bytes = kBTile floats
+    for (int m = 0; m < 37; ++m)
+        for (int n1 = 0; n1 < 7; ++n1) {
+            const int a = (73 * n1 + 7 * m) % kN;
+            const int b = ((73 * n1 - 7 * m) % kN + kN) % kN;
+            w[m * 8 + n1] = static_cast<float>(hann(a));
+            w[(37 + m) * 8 + n1] = m == 0 ? 0.f : static_cast<float>(hann(b));
+        }
+    float* d = nullptr;
+    AFD_CUDA_TRY(cudaMalloc(&d, h.size() * sizeof(float)));
+    AFD_CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    g_tables[dev] = d;
+    *out = d;
+    return AFD_OK;
+}
+
+}  // namespace tc
+
+bool stft_tc511_supported(const float* x, int64_t N, int n_fft, int hop, const float* out) {
+    return n_fft == tc::kN && hop >= 1 && hop <= tc::kMaxHop && N > tc::kN / 2 &&
+           (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 3) == 0;
+}
+
+int stft_tc511_launch(const float* x, int64_t B, int64_t N, int64_t x_row_stride, int hop, float power, int log_scale,
+                      float log_offset, const StftExtras& ex, float* out, cudaStream_t stream) {
+    using namespace tc;
+    int dev = 0;
+    AFD_CUDA_TRY(cudaGetDevice(&dev));
+    float* tables = nullptr;
+    int rc = get_tables(dev, &tables);
+    if (rc != AFD_OK) return rc;
+    Params p;
+    p.hop = hop; p.N = static_cast<int>(N); p.pad = kN / 2;
+    p.frames = static_cast<int>(1 + (N + 2 * (kN / 2) - kN) / hop);
+    p.units_per_row = (p.frames + kRows - 1) / kRows;
+    p.total_units = B * static_cast<long long>(p.units_per_row);
+    p.vec_ok = (reinterpret_cast<uintptr_t>(x) & 15) == 0 ? 1 : 0;
+    p.power = power; p.log_offset = log_offset; p.log_scale = log_scale ? 1 : 0; p.square = (power == 2.0f);
+    p.normalize = ex.normalize; p.nmean = ex.nmean; p.nrstd = ex.nrstd; p.moments = ex.moments; p.store = out != nullptr;
+    const bool ext = ex.normalize || ex.moments || !out;
+    const int mode = p.square ? (p.log_scale ? 0 : 1) : 2;
+    using Kern = void (*)(const float*, long long, float*, const float*, const Params);
+    static const Kern kerns[2][3] = {
+        {stft_tc511_kernel<false, 0>, stft_tc511_kernel<false, 1>, stft_tc511_kernel<false, 2>},
+        {stft_tc511_kernel<true, 0>, stft_tc511_kernel<true, 1>, stft_tc511_kernel<true, 2>}};
+    Kern kern = kerns[ext][mode];
+    static thread_local bool configured[2][3][16] = {};
+    if (dev >= 16 || !configured[ext][mode][dev]) {
+        AFD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        if (dev < 16) configured[ext][mode][dev] = true;
+    }
+    int sms = kNumSmsFallback;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long blocks = p.total_units < sms ? p.total_units : sms;
+    kern<<<static_cast<unsigned>(blocks), kThreads, kSmemBytes, stream>>>(x, static_cast<long long>(x_row_stride), out, tables, p);
+    AFD_CUDA_TRY(cudaGetLastError());
+    return AFD_OK;
+}
+
+}  // namespace afd
