@@ -342,12 +342,13 @@ static int stft_power_impl(const float* x, int64_t B, int64_t N, int64_t x_row_s
     if (N > (1LL << 30)) return fail(AFD_ERR_UNSUPPORTED, "afd_stft_power: signal too long");
     if (B == 0) return AFD_OK;
     {
-        // n_fft = 511 (the reference's 2*num_of_scales-1) takes the prime-factor tensor-core kernel; AFD_STFT_IMPL=bluestein
-        // forces the generic chirp-z kernel (used by the parity tests to cover both).
+        // n_fft = 511 (the reference's 2*num_of_scales-1) takes the prime-factor tensor-core kernels: the tcgen05 / TMEM
+        // kernel (afd_stft_tc.cu); the mma.sync kernel (afd_stft_pfa.cu) is kept as the cross-check.  AFD_STFT_IMPL=pfa forces the mma.sync kernel, AFD_STFT_IMPL=bluestein the generic chirp-z
+        // kernel (the parity tests cover all three).
         const char* impl = getenv("AFD_STFT_IMPL");
         const bool force_generic = impl && strcmp(impl, "bluestein") == 0;
-        const bool want_tc = impl && strcmp(impl, "tc") == 0;
-        if (want_tc && stft_tc511_supported(x, N, n_fft, hop, out))
+        const bool force_pfa = impl && strcmp(impl, "pfa") == 0;
+        if (!force_generic && !force_pfa && stft_tc511_supported(x, N, n_fft, hop, out))
             return stft_tc511_launch(x, B, N, x_row_stride, hop, power, log_scale, log_offset, ex, out,
                                      static_cast<cudaStream_t>(stream));
         if (!force_generic && stft_pfa511_supported(x, N, n_fft, hop, out))

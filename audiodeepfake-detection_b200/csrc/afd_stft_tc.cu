@@ -44,11 +44,10 @@ namespace tc {
 
 constexpr int kN = 511;
 constexpr int kRows = 16;                     // STFT frames per unit
-constexpr int kEpiWarps = 8, kPreWarps = 10;
+constexpr int kEpiWarps = 8, kPreWarps = 19;
 constexpr int kEpiThreads = kEpiWarps * 32;   // 256
-constexpr int kPreThreads = kPreWarps * 32;   // 320
-constexpr int kThreads = kEpiThreads + kPreThreads + 32;   // + MMA warp = 608
-constexpr int kPreSubs = 8;                   // producer thread = (m, sub): rows sub and sub + 8
+constexpr int kPreThreads = kPreWarps * 32;   // 608: one (frame, m) item per thread, 592 used
+constexpr int kThreads = kEpiThreads + kPreThreads + 32;   // + MMA warp = 896
 
 // A tile (bytes): 128 rows x 80 columns of fp32, K-major core matrices
 constexpr int kALbo = 144;                    // distance of consecutive 16-byte K chunks
@@ -62,7 +61,7 @@ constexpr int kRawFloats = 4160;              // >= 15 * hop + 511 + 6  (hop <= 
 constexpr int kMaxHop = (kRawFloats - kN - 6) / (kRows - 1);
 constexpr int kOutStride = 260;               // floats per row of the output tile
 constexpr int kOutFloats = kRows * kOutStride;
-constexpr int kWFloats = 2 * 37 * 8;
+constexpr int kWFloats = 7 * 74;               // window, [n1][m] for the (n1, m) samples then [n1][37 + m] for (n1, 73 - m)
 
 // shared-memory map (bytes)
 constexpr int kOffAHi = 0;
@@ -75,9 +74,10 @@ constexpr int kOffBar = kOffW + kWFloats * 4;                // mbarriers + TMEM
 constexpr int kSmemBytes = kOffBar + 128;
 constexpr int kTableFloats = 4 * kBTile / 4 + kWFloats;      // device table: B tiles (byte-exact smem image) + window
 
-constexpr int kTmemCols = 256;
-constexpr int kDStride = 128;                 // TMEM columns between the two accumulator buffers
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((48u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr int kTmemCols = 512;
+constexpr int kDStride = 256;                 // TMEM columns between the two accumulator buffers (2 parts x 96 used)
+constexpr uint32_t kIdescBase = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);   // f32 accumulate, tf32 x tf32, K-major, M = 128
+constexpr uint32_t kIdesc48 = kIdescBase | ((48u >> 3) << 17), kIdesc96 = kIdescBase | ((96u >> 3) << 17);
 
 struct Params {
     int hop, frames, N, pad, units_per_row, vec_ok;
@@ -101,10 +101,29 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t spin = 0; !done; ++spin) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (spin > (1u << 26)) __trap();       // a lost arrival must not hang the GPU
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");   // suspend-time hint (ns): sleep, do not spin
+        if (spin > (1u << 20)) __trap();       // a lost arrival must not hang the GPU
     }
+}
+#ifdef AFD_TC_PROF
+#define PROF_DECL() long long _pacc[6] = {0, 0, 0, 0, 0, 0}; long long _pt0 = 0
+#define PROF_START() _pt0 = clock64()
+#define PROF_LAP(i) do { const long long _n = clock64(); _pacc[i] += _n - _pt0; _pt0 = _n; } while (0)
+#define PROF_PRINT(cond, what)                                                                                      \
+    if (blockIdx.x == 0 && (cond) && it > 0)                                                                        \
+        printf("tid %d units %d %s: %lld %lld %lld %lld %lld %lld\n", tid, it, what, _pacc[0] / it, _pacc[1] / it,   \
+               _pacc[2] / it, _pacc[3] / it, _pacc[4] / it, _pacc[5] / it)
+#else
+#define PROF_DECL()
+#define PROF_START()
+#define PROF_LAP(i)
+#define PROF_PRINT(cond, what)
+#endif
+// Whole-warp wait: lane 0 polls, the other lanes park at the warp barrier (no issue slots burnt by 31 spinning lanes).
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+    __syncwarp();
 }
 __device__ __forceinline__ void named_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
@@ -114,10 +133,10 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"(accumulate) : "memory");
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
@@ -135,6 +154,22 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
            (static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 
+// Walks the CTA's unit sequence (unit = first, first + stride, ...) as (signal b, first frame t0) without divisions.
+struct UnitWalk {
+    int b, tu;             // signal, unit within the signal
+    int db, dtu, upr;      // stride / units_per_row, stride % units_per_row, units_per_row
+    __device__ __forceinline__ UnitWalk(int first, int stride, int units_per_row) {
+        upr = units_per_row;
+        b = first / upr; tu = first - b * upr;
+        db = stride / upr; dtu = stride - db * upr;
+    }
+    __device__ __forceinline__ void next() {
+        b += db; tu += dtu;
+        if (tu >= upr) { tu -= upr; ++b; }
+    }
+    __device__ __forceinline__ UnitWalk peek() const { UnitWalk n = *this; n.next(); return n; }
+};
+
 // 7-point DFT of a real sequence p[0..6]: r[0] = X0, (r[2j-1], r[2j]) = (Re Xj, Im Xj), j = 1..3.
 __device__ __forceinline__ void dft7_real(const float (&p)[7], float (&r)[7]) {
     constexpr float c1 = 0.62348980185873353f, c2 = -0.22252093395631440f, c3 = -0.90096886790241913f;
@@ -150,31 +185,46 @@ __device__ __forceinline__ void dft7_real(const float (&p)[7], float (&r)[7]) {
     r[6] = -fmaf(s2, b3, fmaf(-s1, b2, s3 * b1));
 }
 
-// Stage the samples of unit (b, t0) into `raw`: raw[aoff + i] = x~[t0*hop - pad + i], x~ = reflect extension.
-__device__ __forceinline__ void stage(const float* __restrict__ xrow, long long g0, float* __restrict__ raw, int t0,
-                                      int valid, const Params& p, int pt) {
-    const int S0 = t0 * p.hop - p.pad;                       // first sample of the unit (may be negative)
+// Staging of a unit's samples: raw[i] = x~[s_begin + i], i in [0, 4 nq), x~ = reflect extension, s_begin = S0 - aoff
+// (S0 = t0 * hop - pad, aoff = misalignment of x~[S0] against 16 bytes; g0 = absolute address of the row in elements).  The 16-byte aligned in-range middle part
+// [lo4, hi4) arrives as ONE bulk copy (TMA engine, full-line shared-memory writes, issued by the MMA thread); the few
+// remaining samples (alignment slack, reflect padding of the first / last unit of a signal) are written by the producers.
+struct StageGeom {
+    int s_begin, lo4, hi4, end;        // sample indices: buffer start, bulk range, buffer end (exclusive)
+};
+__device__ __forceinline__ StageGeom stage_geom(long long g0, int t0, int valid, const Params& p) {
+    StageGeom g;
+    const int S0 = t0 * p.hop - p.pad;
     const int len = (valid - 1) * p.hop + kN;
-    const int aoff = static_cast<int>((g0 + S0) & 3);        // element misalignment of x~[S0]
-    const int nq = (aoff + len + 3) >> 2;
-    const int N = p.N;
-    for (int q = pt; q < nq; q += kPreThreads) {
-        const int s0 = S0 - aoff + 4 * q;
-        float* dst = raw + 4 * q;
-        if (p.vec_ok && s0 >= 0 && s0 + 3 < N) {
-            cp_async_16(dst, xrow + s0);
-        } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                int s = s0 + e;
-                s = s < 0 ? -s : s;
-                s = s >= N ? 2 * (N - 1) - s : s;
-                s = max(0, min(s, N - 1));
-                cp_async_4(dst + e, xrow + s);
-            }
-        }
+    const int aoff = static_cast<int>((g0 + S0) & 3);
+    g.s_begin = S0 - aoff;
+    g.end = g.s_begin + ((aoff + len + 3) & ~3);
+    g.lo4 = g.s_begin < 0 ? g.s_begin + ((-g.s_begin + 3) & ~3) : g.s_begin;
+    const int top = min(g.end, p.N);
+    g.hi4 = g.s_begin + ((top - g.s_begin) & ~3);
+    if (g.hi4 < g.lo4) g.hi4 = g.lo4;
+    return g;
+}
+__device__ __forceinline__ void stage_bulk(const float* __restrict__ xrow, const StageGeom& g, uint32_t raw_addr, uint32_t bar) {
+    const uint32_t bytes = static_cast<uint32_t>(g.hi4 - g.lo4) * 4u;
+    if (bytes) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(raw_addr + static_cast<uint32_t>(g.lo4 - g.s_begin) * 4u), "l"(xrow + g.lo4), "r"(bytes), "r"(bar) : "memory");
+    } else {
+        mbar_arrive(bar);
     }
-    cp_async_commit();
+}
+__device__ __forceinline__ void stage_rest(const float* __restrict__ xrow, const StageGeom& g, float* __restrict__ raw, int N, int pt) {
+    const int nlo = g.lo4 - g.s_begin, nhi = g.end - g.hi4;
+    for (int e = pt; e < nlo + nhi; e += kPreThreads) {
+        const int i = e < nlo ? e : (g.hi4 - g.s_begin) + (e - nlo);
+        int sidx = g.s_begin + i;
+        sidx = sidx < 0 ? -sidx : sidx;
+        sidx = sidx >= N ? 2 * (N - 1) - sidx : sidx;
+        sidx = max(0, min(sidx, N - 1));
+        raw[i] = __ldg(xrow + sidx);
+    }
 }
 
 // MODE 0: power 2 + log (the reference's configuration), 1: power 2, linear, 2: any power / log flag (runtime)
@@ -189,16 +239,19 @@ __device__ __forceinline__ float finish(float re, float im, const Params& p) {
 }
 
 // Epilogue of one unit for the warps of k2 half KH: accumulator columns -> output tile.
+// Accumulator block of a part (Re at +0, Im at +96): columns [0, 48) = A_hi B_hi + A_lo B_hi, [48, 96) = A_hi B_lo.
 template <int MODE, int KH>
 __device__ __forceinline__ void combine(uint32_t taddr, uint32_t bar_d_empty, float* __restrict__ orow, const uint32_t (&binpk)[5],
-                                        bool lane_live, int j, int h, const Params& p) {
+                                        bool lane_live, int h, const Params& p) {
     constexpr int kLo = KH ? 19 : 0, kHi = KH ? 36 : 18;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const int col0 = (KH ? 16 : 0) + 8 * c;
-        float re[8], im[8];
+        float re[8], im[8], re2[8], im2[8];
         tc_ld8(taddr + col0, re);
-        tc_ld8(taddr + 48 + col0, im);
+        tc_ld8(taddr + 48 + col0, re2);
+        tc_ld8(taddr + 96 + col0, im);
+        tc_ld8(taddr + 144 + col0, im2);
         tc_ld_wait();
         if (c == 2) {                          // every accumulator of the unit is in registers: release the buffer
             tc_fence_before();
@@ -208,16 +261,16 @@ __device__ __forceinline__ void combine(uint32_t taddr, uint32_t bar_d_empty, fl
         for (int i = 0; i < 8; ++i) {
             const int k2 = col0 + i;
             if (k2 < kLo || k2 > kHi) continue;
-            const float pre = __shfl_xor_sync(0xffffffffu, re[i], 16);
-            const float pim = __shfl_xor_sync(0xffffffffu, im[i], 16);
-            const float val = finish<MODE>(re[i] - pim, im[i] + pre, p);
+            const float r = re[i] + re2[i], q = im[i] + im2[i];
+            const float pre = __shfl_xor_sync(0xffffffffu, r, 16);
+            const float pim = __shfl_xor_sync(0xffffffffu, q, 16);
+            const float val = finish<MODE>(r - pim, q + pre, p);
             const int idx = k2 - kLo;
             const uint32_t bin = (binpk[idx >> 2] >> (8 * (idx & 3))) & 255u;
             const bool live = lane_live && !(h == 1 && k2 == 0);
             if (live) orow[bin] = val;
         }
     }
-    (void)j;
 }
 
 template <bool EXT, int MODE>
@@ -229,9 +282,11 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
     const int warp = tid >> 5, lane = tid & 31;
     float* const s_w = reinterpret_cast<float*>(smem + kOffW);
     const uint32_t s_base = smem_u32(smem);
-    const uint32_t bar_a_full = s_base + kOffBar, bar_a_free = bar_a_full + 8;
-    const uint32_t bar_d_full = bar_a_full + 16, bar_d_empty = bar_a_full + 32;      // two each
+    const uint32_t bar_p_full = s_base + kOffBar, bar_q_full = bar_p_full + 8;
+    const uint32_t bar_p_free = bar_p_full + 16, bar_q_free = bar_p_full + 24;
+    const uint32_t bar_d_full = bar_p_full + 32, bar_d_empty = bar_p_full + 48;      // two each
     uint32_t* const s_tmem = reinterpret_cast<uint32_t*>(smem + kOffBar + 64);
+    const uint32_t bar_raw_full = bar_p_full + 80;                                     // two: bulk copies of the staging buffers
 
     // ---- one-time setup: tables -> shared memory, A tiles zeroed, barriers, tensor memory
     {
@@ -245,12 +300,16 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
         for (int i = tid; i < (2 * kRawFloats + 2 * kOutFloats) / 4; i += kThreads) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (tid == 0) {
-        mbar_init(bar_a_full, kPreThreads);
-        mbar_init(bar_a_free, 1);
+        mbar_init(bar_p_full, kPreThreads);
+        mbar_init(bar_q_full, kPreThreads);
+        mbar_init(bar_p_free, 1);
+        mbar_init(bar_q_free, 1);
         mbar_init(bar_d_full, 1);
         mbar_init(bar_d_full + 8, 1);
         mbar_init(bar_d_empty, kEpiThreads);
         mbar_init(bar_d_empty + 8, kEpiThreads);
+        mbar_init(bar_raw_full, 1);
+        mbar_init(bar_raw_full + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kThreads / 32 - 1) {
@@ -263,8 +322,11 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
-    const long long first_unit = blockIdx.x;
-    const long long ustride = gridDim.x;
+    const int first_unit = blockIdx.x;                    // total_units < 2^31 (checked on the host)
+    const int ustride = gridDim.x;
+    const int total_units = static_cast<int>(p.total_units);
+    const long long xbase4 = static_cast<long long>(reinterpret_cast<uintptr_t>(x) >> 2);   // rows are aligned by ABSOLUTE address
+    PROF_DECL();
 
     if (warp < kEpiWarps) {
         // ============================================================ epilogue warps
@@ -273,46 +335,71 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
         const bool lane_live = !(h == 1 && j == 0);
         uint32_t binpk[5] = {0u, 0u, 0u, 0u, 0u};
         {
-            const int lo = kh ? 19 : 0, hi = kh ? 36 : 18;
-            for (int k2 = lo; k2 <= hi; ++k2) {
+            const int lo = kh ? 19 : 0, cnt = kh ? 18 : 19;
+#pragma unroll
+            for (int idx = 0; idx < 19; ++idx) {               // compile-time indices keep binpk in registers
+                const int k2 = lo + idx;
                 int kk = (365 * j + 147 * (h ? 73 - k2 : k2)) % kN;
                 kk = kk > 255 ? kN - kk : kk;
-                const int idx = k2 - lo;
-                binpk[idx >> 2] |= static_cast<uint32_t>(kk & 255) << (8 * (idx & 3));
+                if (idx < cnt) binpk[idx >> 2] |= static_cast<uint32_t>(kk & 255) << (8 * (idx & 3));
             }
         }
         float mom_s = 0.f, mom_q = 0.f;
         const float n_rs = (EXT && p.normalize) ? p.nrstd : 1.f, n_dm = (EXT && p.normalize) ? -p.nmean * p.nrstd : 0.f;
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(32 * j) << 16);
         int it = 0;
-        for (long long unit = first_unit; unit < p.total_units; unit += ustride, ++it) {
-            const long long b = unit / p.units_per_row;
-            const int t0 = static_cast<int>(unit - b * p.units_per_row) * kRows;
+        UnitWalk uw(first_unit, ustride, p.units_per_row);
+        for (int unit = first_unit; unit < total_units; unit += ustride, ++it, uw.next()) {
+            const long long b = uw.b;
+            const int t0 = uw.tu * kRows;
             const int valid = min(kRows, p.frames - t0);
             const int buf = it & 1;
             float* const s_out = reinterpret_cast<float*>(smem + kOffOut) + buf * kOutFloats;
-            mbar_wait(bar_d_full + 8 * buf, (it >> 1) & 1);
+            PROF_START();
+            mbar_wait_warp(bar_d_full + 8 * buf, (it >> 1) & 1);
+            PROF_LAP(0);
             tc_fence_after();
             const uint32_t taddr = lane_addr + buf * kDStride;
-            if (kh == 0) combine<MODE, 0>(taddr, bar_d_empty + 8 * buf, s_out + f * kOutStride, binpk, lane_live, j, h, p);
-            else combine<MODE, 1>(taddr, bar_d_empty + 8 * buf, s_out + f * kOutStride, binpk, lane_live, j, h, p);
+            if (kh == 0) combine<MODE, 0>(taddr, bar_d_empty + 8 * buf, s_out + f * kOutStride, binpk, lane_live, h, p);
+            else combine<MODE, 1>(taddr, bar_d_empty + 8 * buf, s_out + f * kOutStride, binpk, lane_live, h, p);
+            PROF_LAP(1);
+            if constexpr (!EXT) {
+                // plain features: the valid rows leave as bulk copies (one 1 KB row per lane of warp 0), asynchronously
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // tile writes -> async proxy
+                if (warp == 0 && lane < kRows) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // unit it-1's rows are out of the other tile
+                named_bar(1, kEpiThreads);                       // the unit's tile is complete; the other tile is free
+                PROF_LAP(2);
+                if (warp == 0 && lane < kRows) {
+                    if (lane < valid) {
+                        float* og = out + (b * p.frames + t0 + lane) * 256LL;
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 1024;"
+                                     ::"l"(og), "r"(smem_u32(s_out + lane * kOutStride)) : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else {
             named_bar(1, kEpiThreads);                           // the unit's tile is complete
+            PROF_LAP(2);
             float* og = out + (b * p.frames + t0) * 256LL;
             for (int i = tid; i < valid * 64; i += kEpiThreads) {
                 const int row = i >> 6, c4 = (i & 63) * 4;
                 float4 v = *reinterpret_cast<const float4*>(s_out + row * kOutStride + c4);
-                if (EXT && p.moments) {
+                if (p.moments) {
                     mom_s += (v.x + v.y) + (v.z + v.w);
                     mom_q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, mom_q))));
                 }
-                if (EXT && p.normalize) {
+                if (p.normalize) {
                     v.x = fmaf(v.x, n_rs, n_dm); v.y = fmaf(v.y, n_rs, n_dm);
                     v.z = fmaf(v.z, n_rs, n_dm); v.w = fmaf(v.w, n_rs, n_dm);
                 }
-                if (!EXT || p.store) st_cs4(reinterpret_cast<float4*>(og + row * 256 + c4), v);
+                if (p.store) st_cs4(reinterpret_cast<float4*>(og + row * 256 + c4), v);
             }
+            }
+            PROF_LAP(3);
             // the other tile is rewritten only after every thread passed the next unit's barrier
         }
+        if (!EXT && warp == 0 && lane < kRows) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        PROF_PRINT(tid == 0 || tid == 133, "epi: wait d_full / combine / bar / store");
         if (EXT && p.moments) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -325,13 +412,16 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
             }
         }
     } else if (warp < kEpiWarps + kPreWarps) {
-        // ============================================================ producer warps
+        // ============================================================ producer warps: thread = (frame r, column m)
+        // warps 0..15: frame r = warp, m = lane (0..31): data, window and A-tile accesses of a warp walk along m and are
+        // bank-conflict free; warps 16..18: the remaining m = 32..36 of all 16 frames (80 items).
         const int pt = tid - kEpiThreads;
-        const bool active = pt < 37 * kPreSubs;
-        const int pm = pt % 37;
-        const int psub = pt / 37;
+        const int pw = pt >> 5;
+        const int pe = (pw - 16) * 32 + lane;
+        const bool active = pw < 16 || pe < 5 * kRows;
+        const int r = pw < 16 ? pw : (pe < 5 * kRows ? pe / 5 : 0);
+        const int pm = pw < 16 ? lane : (pe < 5 * kRows ? 32 + pe % 5 : 0);
         int offA[7], offB[7];
-        float wA[7], wB[7];
 #pragma unroll
         for (int n1 = 0; n1 < 7; ++n1) {
             int a = 73 * n1 + 7 * pm;
@@ -340,108 +430,127 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
             bq = bq < 0 ? bq + kN : bq;
             offA[n1] = a;
             offB[n1] = bq;
-            wA[n1] = s_w[pm * 8 + n1];
-            wB[n1] = s_w[(37 + pm) * 8 + n1];
         }
-        unsigned char* const a_hi = smem + kOffAHi + (pm >> 2) * kALbo + (pm & 3) * 4;     // column m of the P block
+        const float* const wA = s_w + pm;                      // [n1 * 74]: lanes walk along m -> conflict-free
+        const float* const wB = s_w + 37 + pm;
+        unsigned char* const arow = smem + kOffAHi + (pm >> 2) * kALbo + (pm & 3) * 4 + (r & 7) * 16 + (r >> 3) * kASbo;
         constexpr int kQ = 10 * kALbo;                                                      // column 40 + m
         float* const raw0 = reinterpret_cast<float*>(smem + kOffRaw);
-        if (first_unit < p.total_units) {
-            const long long b = first_unit / p.units_per_row;
-            const int t0 = static_cast<int>(first_unit - b * p.units_per_row) * kRows;
-            stage(x + b * x_row_stride, b * x_row_stride, raw0, t0, min(kRows, p.frames - t0), p, pt);
+        UnitWalk uw(first_unit, ustride, p.units_per_row);
+        if (first_unit < total_units) {
+            const long long g0 = uw.b * x_row_stride;
+            stage_rest(x + g0, stage_geom(xbase4 + g0, uw.tu * kRows, min(kRows, p.frames - uw.tu * kRows), p), raw0, p.N, pt);
         }
         int it = 0;
-        for (long long unit = first_unit; unit < p.total_units; unit += ustride, ++it) {
-            const long long b = unit / p.units_per_row;
-            const int t0 = static_cast<int>(unit - b * p.units_per_row) * kRows;
+        for (int unit = first_unit; unit < total_units; unit += ustride, ++it, uw.next()) {
+            const int t0 = uw.tu * kRows;
             const int valid = min(kRows, p.frames - t0);
-            const int aoff = static_cast<int>((b * x_row_stride + (t0 * p.hop - p.pad)) & 3);
+            const int aoff = (static_cast<int>(xbase4 + uw.b * x_row_stride) + (t0 * p.hop - p.pad)) & 3;
             const float* raw = raw0 + (it & 1) * kRawFloats;
-            cp_async_wait<0>();
-            named_bar(2, kPreThreads);                           // samples landed; the other buffer is no longer read
+            PROF_START();
+            mbar_wait_warp(bar_raw_full + 8 * (it & 1), (it >> 1) & 1);     // the unit's bulk copy has landed
+            named_bar(2, kPreThreads);                           // ... and its edge samples; the other buffer is no longer read
+            PROF_LAP(0);
             {
-                const long long nu = unit + ustride;
-                if (nu < p.total_units) {
-                    const long long nb = nu / p.units_per_row;
-                    const int nt0 = static_cast<int>(nu - nb * p.units_per_row) * kRows;
-                    stage(x + nb * x_row_stride, nb * x_row_stride, raw0 + ((it + 1) & 1) * kRawFloats, nt0,
-                          min(kRows, p.frames - nt0), p, pt);
+                if (unit + ustride < total_units) {
+                    const UnitWalk nw = uw.peek();
+                    const long long g0 = nw.b * x_row_stride;
+                    stage_rest(x + g0, stage_geom(xbase4 + g0, nw.tu * kRows, min(kRows, p.frames - nw.tu * kRows), p),
+                               raw0 + ((it + 1) & 1) * kRawFloats, p.N, pt);
                 }
             }
-            // both rows of the thread are computed BEFORE the A tiles are claimed: this overlaps the previous unit's MMAs
-            float P[2][7], Q[2][7];
+            // the row is computed BEFORE the A tiles are claimed: this overlaps the previous unit's MMAs
+            const bool live = active && r < valid;
+            float P[7], Q[7];
+            if (live) {
+                const float* fr = raw + aoff + r * p.hop;
+                float pp[7], qq[7];
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int r = psub + rr * kPreSubs;
-                if (active && r < valid) {
-                    const float* fr = raw + aoff + r * p.hop;
-                    float pp[7], qq[7];
-#pragma unroll
-                    for (int n1 = 0; n1 < 7; ++n1) {
-                        const float xa = fr[offA[n1]] * wA[n1];
-                        const float xb = fr[offB[n1]] * wB[n1];
-                        pp[n1] = xa + xb;
-                        qq[n1] = xa - xb;
-                    }
-                    dft7_real(pp, P[rr]);
-                    dft7_real(qq, Q[rr]);
+                for (int n1 = 0; n1 < 7; ++n1) {
+                    const float xa = fr[offA[n1]] * wA[74 * n1];
+                    const float xb = fr[offB[n1]] * wB[74 * n1];
+                    pp[n1] = xa + xb;
+                    qq[n1] = xa - xb;
                 }
+                dft7_real(pp, P);
+                dft7_real(qq, Q);
             }
-            if (it > 0) mbar_wait(bar_a_free, (it - 1) & 1);     // the previous unit's MMAs have read the A tiles
+            PROF_LAP(1);
+            if (it > 0) mbar_wait_warp(bar_p_free, (it - 1) & 1);     // the previous unit's Re MMAs have read the P block
+            PROF_LAP(2);
+            if (live) {
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int r = psub + rr * kPreSubs;
-                if (active && r < valid) {
-                    unsigned char* arow = a_hi + (r & 7) * 16 + (r >> 3) * kASbo;
-#pragma unroll
-                    for (int s = 0; s < 7; ++s) {
-                        const int row8 = s == 0 ? 0 : 4 * ((s + 1) >> 1) + 2 * ((s + 1) & 1);   // (32 j + 16 h) / 8
-                        {
-                            const float hi = __uint_as_float(__float_as_uint(P[rr][s]) & 0xffffe000u);
-                            *reinterpret_cast<float*>(arow + row8 * kASbo) = hi;
-                            *reinterpret_cast<float*>(arow + row8 * kASbo + kATile) = P[rr][s] - hi;
-                        }
-                        if (pm != 0) {
-                            const float hi = __uint_as_float(__float_as_uint(Q[rr][s]) & 0xffffe000u);
-                            *reinterpret_cast<float*>(arow + row8 * kASbo + kQ) = hi;
-                            *reinterpret_cast<float*>(arow + row8 * kASbo + kQ + kATile) = Q[rr][s] - hi;
-                        }
-                    }
+                for (int s = 0; s < 7; ++s) {
+                    const int row8 = s == 0 ? 0 : 4 * ((s + 1) >> 1) + 2 * ((s + 1) & 1);   // (32 j + 16 h) / 8
+                    const float hi = __uint_as_float(__float_as_uint(P[s]) & 0xffffe000u);
+                    *reinterpret_cast<float*>(arow + row8 * kASbo) = hi;
+                    *reinterpret_cast<float*>(arow + row8 * kASbo + kATile) = P[s] - hi;
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(bar_a_full);
+            mbar_arrive(bar_p_full);
+            PROF_LAP(3);
+            if (it > 0) mbar_wait_warp(bar_q_free, (it - 1) & 1);     // ... the Im MMAs the Q block
+            PROF_LAP(4);
+            if (live && pm != 0) {
+#pragma unroll
+                for (int s = 0; s < 7; ++s) {
+                    const int row8 = s == 0 ? 0 : 4 * ((s + 1) >> 1) + 2 * ((s + 1) & 1);
+                    const float hi = __uint_as_float(__float_as_uint(Q[s]) & 0xffffe000u);
+                    *reinterpret_cast<float*>(arow + row8 * kASbo + kQ) = hi;
+                    *reinterpret_cast<float*>(arow + row8 * kASbo + kQ + kATile) = Q[s] - hi;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(bar_q_full);
+            PROF_LAP(5);
         }
-        cp_async_wait<0>();
+        PROF_PRINT(pt == 0 || pt == 300, "pre: raw wait+bar / stage+compute / wait p_free / sts P / wait q_free / sts Q");
     } else if (lane == 0) {
         // ============================================================ MMA issuer (one thread)
         const uint32_t a_hi = s_base + kOffAHi, a_lo = s_base + kOffALo;
         const uint32_t b0 = s_base + kOffB;
+        const uint32_t raw_addr = s_base + kOffRaw;
+        UnitWalk lw(first_unit, ustride, p.units_per_row);       // walks two units ahead: the staging loads
+        auto load_unit = [&](int n) {                            // bulk copy of the CTA's n-th unit into buffer n & 1
+            const long long g0 = lw.b * x_row_stride;
+            stage_bulk(x + g0, stage_geom(xbase4 + g0, lw.tu * kRows, min(kRows, p.frames - lw.tu * kRows), p),
+                       raw_addr + (n & 1) * kRawFloats * 4, bar_raw_full + 8 * (n & 1));
+            lw.next();
+        };
+        if (first_unit < total_units) load_unit(0);
+        if (first_unit + ustride < total_units) load_unit(1);
         int it = 0;
-        for (long long unit = first_unit; unit < p.total_units; unit += ustride, ++it) {
+        for (int unit = first_unit; unit < total_units; unit += ustride, ++it) {
             const int buf = it & 1;
-            mbar_wait(bar_a_full, it & 1);
-            if (it >= 2) mbar_wait(bar_d_empty + 8 * buf, ((it >> 1) - 1) & 1);
-            tc_fence_after();
 #pragma unroll
             for (int part = 0; part < 2; ++part) {               // 0: Re = P x C, 1: Im = Q x S
-                const uint32_t d = tmem_base + buf * kDStride + part * 48;
-                const uint32_t bh = b0 + (2 * part) * kBTile, bl = bh + kBTile;
+                PROF_START();
+                mbar_wait(part ? bar_q_full : bar_p_full, it & 1);
+                if (part == 0) {
+                    // p_full(it): every producer has finished reading staging buffer it & 1 -> refill it for unit it + 2
+                    if (static_cast<long long>(unit) + 2LL * ustride < total_units) load_unit(it + 2);
+                    if (it >= 2) mbar_wait(bar_d_empty + 8 * buf, ((it >> 1) - 1) & 1);
+                }
+                PROF_LAP(2 * part);
+                tc_fence_after();
+                const uint32_t d = tmem_base + buf * kDStride + part * 96;
+                const uint32_t bh = b0 + (2 * part) * kBTile;     // [hi tile | lo tile] = 96 rows of one N = 96 operand
                 const uint32_t ak = part * 10 * kALbo;
 #pragma unroll
-                for (int term = 0; term < 3; ++term) {           // small terms first: lo*hi, hi*lo, hi*hi
-                    const uint32_t at = (term == 0 ? a_lo : a_hi) + ak;
-                    const uint32_t bt = term == 1 ? bl : bh;
+                for (int ks = 0; ks < 5; ++ks)                   // A_hi x [B_hi | B_lo] -> columns [0, 96)
+                    tc_mma_tf32(d, make_desc(a_hi + ak + 2 * ks * kALbo, kALbo, kASbo), make_desc(bh + 2 * ks * kBLbo, kBLbo, kBSbo),
+                                kIdesc96, ks != 0);
 #pragma unroll
-                    for (int ks = 0; ks < 5; ++ks)
-                        tc_mma_tf32(d, make_desc(at + 2 * ks * kALbo, kALbo, kASbo), make_desc(bt + 2 * ks * kBLbo, kBLbo, kBSbo),
-                                    (term | ks) != 0);
-                }
+                for (int ks = 0; ks < 5; ++ks)                   // A_lo x B_hi -> columns [0, 48)
+                    tc_mma_tf32(d, make_desc(a_lo + ak + 2 * ks * kALbo, kALbo, kASbo), make_desc(bh + 2 * ks * kBLbo, kBLbo, kBSbo),
+                                kIdesc48, 1);
+                tc_commit(part ? bar_q_free : bar_p_free);
+                if (part == 1) tc_commit(bar_d_full + 8 * buf);
+                PROF_LAP(2 * part + 1);
             }
-            tc_commit(bar_a_free);
-            tc_commit(bar_d_full + 8 * buf);
         }
+        PROF_PRINT(true, "mma: wait p_full(+d_empty) / issue Re / wait q_full / issue Im");
     }
     // ---- teardown
     tc_fence_before();
@@ -493,8 +602,8 @@ static int get_tables(int dev, float** out) {
         for (int n1 = 0; n1 < 7; ++n1) {
             const int a = (73 * n1 + 7 * m) % kN;
             const int b = ((73 * n1 - 7 * m) % kN + kN) % kN;
-            w[m * 8 + n1] = static_cast<float>(hann(a));
-            w[(37 + m) * 8 + n1] = m == 0 ? 0.f : static_cast<float>(hann(b));
+            w[n1 * 74 + m] = static_cast<float>(hann(a));
+            w[n1 * 74 + 37 + m] = m == 0 ? 0.f : static_cast<float>(hann(b));
         }
     float* d = nullptr;
     AFD_CUDA_TRY(cudaMalloc(&d, h.size() * sizeof(float)));
@@ -524,6 +633,7 @@ int stft_tc511_launch(const float* x, int64_t B, int64_t N, int64_t x_row_stride
     p.frames = static_cast<int>(1 + (N + 2 * (kN / 2) - kN) / hop);
     p.units_per_row = (p.frames + kRows - 1) / kRows;
     p.total_units = B * static_cast<long long>(p.units_per_row);
+    if (p.total_units >= (1LL << 31) - 65536) return fail(AFD_ERR_UNSUPPORTED, "afd_stft_power: batch too large for one launch");
     p.vec_ok = (reinterpret_cast<uintptr_t>(x) & 15) == 0 ? 1 : 0;
     p.power = power; p.log_offset = log_offset; p.log_scale = log_scale ? 1 : 0; p.square = (power == 2.0f);
     p.normalize = ex.normalize; p.nmean = ex.nmean; p.nrstd = ex.nrstd; p.moments = ex.moments; p.store = out != nullptr;

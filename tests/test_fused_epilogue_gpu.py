@@ -137,13 +137,13 @@ def test_welford_dict_accumulates_over_batches():
         assert float(d[keys[p]].count) == col.size
 
 
-@pytest.mark.parametrize("impl", ["pfa", "bluestein"])
+@pytest.mark.parametrize("impl", ["tc", "pfa", "bluestein"])
 def test_stft_fused_normalize_and_moments(impl):
     x = _frames(5, seed=11)
     xt = torch.from_numpy(x).cuda()
     old = os.environ.get("AFD_STFT_IMPL")
-    if impl == "bluestein":
-        os.environ["AFD_STFT_IMPL"] = "bluestein"
+    if impl != "tc":                                  # "tc" = the default dispatch (tcgen05 kernel)
+        os.environ["AFD_STFT_IMPL"] = impl
     try:
         plain = afd.stft_power_features(xt, log_scale=True)
         mom = torch.zeros((1, 2), dtype=torch.float64, device="cuda")

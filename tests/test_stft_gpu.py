@@ -89,16 +89,27 @@ def test_parseval_full_batch(cuda_device):
     assert torch.equal(spec, afd.stft_power_features(x))               # bitwise reproducible
 
 
+def _select(monkeypatch, impl):
+    """None: default dispatch (tcgen05 kernel), "pfa": the mma.sync kernel."""
+    if impl is None:
+        monkeypatch.delenv("AFD_STFT_IMPL", raising=False)
+    else:
+        monkeypatch.setenv("AFD_STFT_IMPL", impl)
+
+
+@pytest.mark.parametrize("impl", [None, "pfa"])
 @pytest.mark.parametrize("hop,N,B", [(220, 22050, 37), (100, 8000, 3), (242, 22050, 2), (1, 700, 2), (243, 22050, 2),
-                                     (220, 256, 3), (220, 3000, 17)])
-def test_pfa511_tensor_core_path(hop, N, B, cuda_device, monkeypatch):
-    """n_fft = 511 takes the prime-factor / tensor-core kernel (hop <= 242): fp64 DFT parity, and agreement with the
-    generic chirp-z kernel forced through AFD_STFT_IMPL=bluestein (hop 243 is served by the generic kernel anyway)."""
+                                     (220, 256, 3), (220, 3000, 17), (220, 22050, 300)])
+def test_pfa511_tensor_core_path(hop, N, B, impl, cuda_device, monkeypatch):
+    """n_fft = 511 takes the prime-factor / tensor-core kernels (hop <= 242; tcgen05 by default, mma.sync with
+    AFD_STFT_IMPL=pfa): fp64 DFT parity, and agreement with the generic chirp-z kernel forced through
+    AFD_STFT_IMPL=bluestein (hop 243 is served by the generic kernel anyway).  B = 300 gives every persistent CTA
+    several units (pipeline phases wrap)."""
     rng = np.random.default_rng(hop * 7 + N)
     x = (rng.standard_normal((B, N)) * 0.1).astype(np.float32)
     want = ptwt_like.stft_power_explicit(torch.from_numpy(x).double().unsqueeze(1), 511, hop).numpy()
     xt = torch.from_numpy(x).to(cuda_device)
-    monkeypatch.delenv("AFD_STFT_IMPL", raising=False)
+    _select(monkeypatch, impl)
     got = afd.stft_power_features(xt, 511, hop).cpu().numpy()
     assert got.shape == want[:, :, :, :].transpose(0, 1, 3, 2).shape
     assert _rel(got, want.transpose(0, 1, 3, 2)) < TOL
@@ -107,10 +118,12 @@ def test_pfa511_tensor_core_path(hop, N, B, cuda_device, monkeypatch):
     assert _rel(got, other) < TOL
 
 
-def test_pfa511_misaligned_rows(cuda_device, monkeypatch):
+@pytest.mark.parametrize("impl", [None, "pfa"])
+def test_pfa511_misaligned_rows(impl, cuda_device, monkeypatch):
     """Rows that start at every 4-byte phase (views into a larger buffer): the staging copy falls back from 16-byte to
-    element-wise cp.async and the result must not change."""
-    monkeypatch.delenv("AFD_STFT_IMPL", raising=False)
+    element-wise cp.async (mma.sync kernel) / the bulk copies start at the enclosing 16-byte boundary and the edge samples
+    are written separately (tcgen05 kernel), and the result must not change."""
+    _select(monkeypatch, impl)
     g = torch.Generator(device="cuda").manual_seed(11)
     big = torch.randn(6, 22050 + 7, device=cuda_device, generator=g) * 0.1
     base = afd.stft_power_features(big[:, :22050].contiguous())
@@ -122,8 +135,9 @@ def test_pfa511_misaligned_rows(cuda_device, monkeypatch):
     assert torch.isfinite(base).all()
 
 
-def test_pfa511_log_and_power(cuda_device, monkeypatch):
-    monkeypatch.delenv("AFD_STFT_IMPL", raising=False)
+@pytest.mark.parametrize("impl", [None, "pfa"])
+def test_pfa511_log_and_power(impl, cuda_device, monkeypatch):
+    _select(monkeypatch, impl)
     rng = np.random.default_rng(5)
     x = (rng.standard_normal((3, 22050)) * 0.1).astype(np.float32)
     truth = ptwt_like.stft_power_dft64(x).transpose(0, 2, 1)                # [B, frames, bins] fp64

@@ -7,7 +7,7 @@ import sys
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = ctypes.CDLL(os.path.join(ROOT, "audiodeepfake-detection_b200", "libafd_b200.so"))
+lib = ctypes.CDLL(os.environ.get("AFD_LIB") or os.path.join(ROOT, "audiodeepfake-detection_b200", "libafd_b200.so"))
 lib.afd_last_error.restype = ctypes.c_char_p
 
 
