@@ -7,7 +7,8 @@
 // of the reference (wavelet_math.py:47,63-66).  Algorithm (fold, DFT-7, DFT-73 as two real GEMMs against cos / -sin,
 // combine): see the header of afd_stft_pfa.cu; the arithmetic outside the GEMM is the same.
 //
-// Mapping.  A unit = 16 consecutive STFT frames of one signal.  Its seven real sequences (u0, u1, v1, u2, v2, u3, v3)
+// Mapping.  A unit = 16 consecutive rows of the flattened (signal, frame) index, i.e. 16 consecutive output rows; it may
+// straddle two signals (two staged sample segments), so only the last unit of a launch is partial.  Its seven real sequences (u0, u1, v1, u2, v2, u3, v3)
 // are the rows of ONE 128-row MMA tile: row = 32 j + 16 h + f  (j = 0..3, h = 0: u_j / 1: v_j, f = frame; rows
 // 16..31 stay zero), columns = [P (m = 0..36, padded to 40) | Q (m = 1..36 at 41..76, padded to 80)].
 //     D[:, 0:48]  = A[:, 0:40]  x C      (Re part, C[m][k2] =  cos(2 pi m k2 / 73), N padded 37 -> 48)
@@ -57,8 +58,8 @@ constexpr int kATile = 16 * kASbo;            // 46080
 constexpr int kBLbo = 128;
 constexpr int kBSbo = 10 * kBLbo;             // 1280
 constexpr int kBTile = 6 * kBSbo;             // 7680
-constexpr int kRawFloats = 4160;              // >= 15 * hop + 511 + 6  (hop <= 242)
-constexpr int kMaxHop = (kRawFloats - kN - 6) / (kRows - 1);
+constexpr int kRawFloats = 4432;              // two segments: >= 14 * hop + 2 * (511 + 6)  (hop <= 242); one: 15 * hop + 517
+constexpr int kMaxHop = (kRawFloats - 2 * (kN + 6)) / (kRows - 2);
 constexpr int kOutStride = 260;               // floats per row of the output tile
 constexpr int kOutFloats = kRows * kOutStride;
 constexpr int kWFloats = 7 * 74;               // window, [n1][m] for the (n1, m) samples then [n1][37 + m] for (n1, 73 - m)
@@ -80,8 +81,8 @@ constexpr uint32_t kIdescBase = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4
 constexpr uint32_t kIdesc48 = kIdescBase | ((48u >> 3) << 17), kIdesc96 = kIdescBase | ((96u >> 3) << 17);
 
 struct Params {
-    int hop, frames, N, pad, units_per_row, vec_ok;
-    long long total_units;
+    int hop, frames, N, pad, B;
+    long long total_units, total_rows;
     float power, log_offset;
     int log_scale, square;
     int normalize, store;
@@ -154,20 +155,24 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
            (static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 
-// Walks the CTA's unit sequence (unit = first, first + stride, ...) as (signal b, first frame t0) without divisions.
+// Walks the CTA's unit sequence (unit = first, first + stride, ...): (signal b, frame t) of the unit's first row, without
+// divisions in the loop.  A unit holds n0 = min(16, frames - t) rows of signal b and, when b + 1 exists, 16 - n0 rows of b + 1.
 struct UnitWalk {
-    int b, tu;             // signal, unit within the signal
-    int db, dtu, upr;      // stride / units_per_row, stride % units_per_row, units_per_row
-    __device__ __forceinline__ UnitWalk(int first, int stride, int units_per_row) {
-        upr = units_per_row;
-        b = first / upr; tu = first - b * upr;
-        db = stride / upr; dtu = stride - db * upr;
+    int b, t;
+    int db, dt, frames;
+    __device__ __forceinline__ UnitWalk(int first, int stride, int frames_) {
+        frames = frames_;
+        const long long G = static_cast<long long>(first) * kRows, D = static_cast<long long>(stride) * kRows;
+        b = static_cast<int>(G / frames); t = static_cast<int>(G - static_cast<long long>(b) * frames);
+        db = static_cast<int>(D / frames); dt = static_cast<int>(D - static_cast<long long>(db) * frames);
     }
     __device__ __forceinline__ void next() {
-        b += db; tu += dtu;
-        if (tu >= upr) { tu -= upr; ++b; }
+        b += db; t += dt;
+        if (t >= frames) { t -= frames; ++b; }
     }
     __device__ __forceinline__ UnitWalk peek() const { UnitWalk n = *this; n.next(); return n; }
+    __device__ __forceinline__ int n0() const { return min(kRows, frames - t); }
+    __device__ __forceinline__ int n1(int B) const { return b + 1 < B ? kRows - n0() : 0; }
 };
 
 // 7-point DFT of a real sequence p[0..6]: r[0] = X0, (r[2j-1], r[2j]) = (Re Xj, Im Xj), j = 1..3.
@@ -205,17 +210,27 @@ __device__ __forceinline__ StageGeom stage_geom(long long g0, int t0, int valid,
     if (g.hi4 < g.lo4) g.hi4 = g.lo4;
     return g;
 }
-__device__ __forceinline__ void stage_bulk(const float* __restrict__ xrow, const StageGeom& g, uint32_t raw_addr, uint32_t bar) {
-    const uint32_t bytes = static_cast<uint32_t>(g.hi4 - g.lo4) * 4u;
-    if (bytes) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+__device__ __forceinline__ uint32_t bulk_bytes(const StageGeom& g) { return static_cast<uint32_t>(g.hi4 - g.lo4) * 4u; }
+__device__ __forceinline__ void bulk_issue(const float* __restrict__ xrow, const StageGeom& g, uint32_t raw_addr, uint32_t bar) {
+    if (bulk_bytes(g))
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(raw_addr + static_cast<uint32_t>(g.lo4 - g.s_begin) * 4u), "l"(xrow + g.lo4), "r"(bytes), "r"(bar) : "memory");
-    } else {
-        mbar_arrive(bar);
-    }
+                     ::"r"(raw_addr + static_cast<uint32_t>(g.lo4 - g.s_begin) * 4u), "l"(xrow + g.lo4), "r"(bulk_bytes(g)), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void stage_rest(const float* __restrict__ xrow, const StageGeom& g, float* __restrict__ raw, int N, int pt) {
+// Both segments of a unit: one arrival carrying the byte count, then the (up to) two bulk copies.  One thread.
+__device__ __forceinline__ void stage_bulk(const float* __restrict__ x, long long xbase4, long long stride, const UnitWalk& w,
+                                           const Params& p, uint32_t raw_addr, uint32_t bar) {
+    const long long g0 = w.b * stride;
+    const StageGeom a = stage_geom(xbase4 + g0, w.t, w.n0(), p);
+    const int n1 = w.n1(p.B);
+    StageGeom c = a;
+    if (n1 > 0) c = stage_geom(xbase4 + g0 + stride, 0, n1, p);
+    const uint32_t bytes = bulk_bytes(a) + (n1 > 0 ? bulk_bytes(c) : 0u);
+    if (bytes) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    else mbar_arrive(bar);
+    bulk_issue(x + g0, a, raw_addr, bar);
+    if (n1 > 0) bulk_issue(x + g0 + stride, c, raw_addr + static_cast<uint32_t>(a.end - a.s_begin) * 4u, bar);
+}
+__device__ __forceinline__ void rest_one(const float* __restrict__ xrow, const StageGeom& g, float* __restrict__ raw, int N, int pt) {
     const int nlo = g.lo4 - g.s_begin, nhi = g.end - g.hi4;
     for (int e = pt; e < nlo + nhi; e += kPreThreads) {
         const int i = e < nlo ? e : (g.hi4 - g.s_begin) + (e - nlo);
@@ -225,6 +240,15 @@ __device__ __forceinline__ void stage_rest(const float* __restrict__ xrow, const
         sidx = max(0, min(sidx, N - 1));
         raw[i] = __ldg(xrow + sidx);
     }
+}
+// The samples the bulk copies leave out (alignment slack, reflect padding).  All producer threads.
+__device__ __forceinline__ void stage_rest(const float* __restrict__ x, long long xbase4, long long stride, const UnitWalk& w,
+                                           const Params& p, float* __restrict__ raw, int pt) {
+    const long long g0 = w.b * stride;
+    const StageGeom a = stage_geom(xbase4 + g0, w.t, w.n0(), p);
+    rest_one(x + g0, a, raw, p.N, pt);
+    const int n1 = w.n1(p.B);
+    if (n1 > 0) rest_one(x + g0 + stride, stage_geom(xbase4 + g0 + stride, 0, n1, p), raw + (a.end - a.s_begin), p.N, pt);
 }
 
 // MODE 0: power 2 + log (the reference's configuration), 1: power 2, linear, 2: any power / log flag (runtime)
@@ -348,11 +372,9 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
         const float n_rs = (EXT && p.normalize) ? p.nrstd : 1.f, n_dm = (EXT && p.normalize) ? -p.nmean * p.nrstd : 0.f;
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(32 * j) << 16);
         int it = 0;
-        UnitWalk uw(first_unit, ustride, p.units_per_row);
-        for (int unit = first_unit; unit < total_units; unit += ustride, ++it, uw.next()) {
-            const long long b = uw.b;
-            const int t0 = uw.tu * kRows;
-            const int valid = min(kRows, p.frames - t0);
+        for (int unit = first_unit; unit < total_units; unit += ustride, ++it) {
+            const long long G0 = static_cast<long long>(unit) * kRows;      // first output row of the unit
+            const int valid = static_cast<int>(min(static_cast<long long>(kRows), p.total_rows - G0));
             const int buf = it & 1;
             float* const s_out = reinterpret_cast<float*>(smem + kOffOut) + buf * kOutFloats;
             PROF_START();
@@ -371,7 +393,7 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
                 PROF_LAP(2);
                 if (warp == 0 && lane < kRows) {
                     if (lane < valid) {
-                        float* og = out + (b * p.frames + t0 + lane) * 256LL;
+                        float* og = out + (G0 + lane) * 256LL;
                         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 1024;"
                                      ::"l"(og), "r"(smem_u32(s_out + lane * kOutStride)) : "memory");
                     }
@@ -380,7 +402,7 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
             } else {
             named_bar(1, kEpiThreads);                           // the unit's tile is complete
             PROF_LAP(2);
-            float* og = out + (b * p.frames + t0) * 256LL;
+            float* og = out + G0 * 256LL;
             for (int i = tid; i < valid * 64; i += kEpiThreads) {
                 const int row = i >> 6, c4 = (i & 63) * 4;
                 float4 v = *reinterpret_cast<const float4*>(s_out + row * kOutStride + c4);
@@ -436,34 +458,32 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
         unsigned char* const arow = smem + kOffAHi + (pm >> 2) * kALbo + (pm & 3) * 4 + (r & 7) * 16 + (r >> 3) * kASbo;
         constexpr int kQ = 10 * kALbo;                                                      // column 40 + m
         float* const raw0 = reinterpret_cast<float*>(smem + kOffRaw);
-        UnitWalk uw(first_unit, ustride, p.units_per_row);
-        if (first_unit < total_units) {
-            const long long g0 = uw.b * x_row_stride;
-            stage_rest(x + g0, stage_geom(xbase4 + g0, uw.tu * kRows, min(kRows, p.frames - uw.tu * kRows), p), raw0, p.N, pt);
-        }
+        UnitWalk uw(first_unit, ustride, p.frames);
+        if (first_unit < total_units) stage_rest(x, xbase4, x_row_stride, uw, p, raw0, pt);
         int it = 0;
         for (int unit = first_unit; unit < total_units; unit += ustride, ++it, uw.next()) {
-            const int t0 = uw.tu * kRows;
-            const int valid = min(kRows, p.frames - t0);
-            const int aoff = (static_cast<int>(xbase4 + uw.b * x_row_stride) + (t0 * p.hop - p.pad)) & 3;
+            const int n0 = uw.n0();
+            const int valid = n0 + uw.n1(p.B);
+            // where the thread's frame starts in the staging buffer: segment 0 (signal b) or segment 1 (signal b + 1)
+            const int abs0 = static_cast<int>(xbase4 + uw.b * x_row_stride);
+            const int aoff0 = (abs0 + (uw.t * p.hop - p.pad)) & 3;
+            const int off1 = (aoff0 + (n0 - 1) * p.hop + kN + 3) & ~3;
+            const int aoff1 = (abs0 + static_cast<int>(x_row_stride) - p.pad) & 3;
+            const int fr_off = r < n0 ? aoff0 + r * p.hop : off1 + aoff1 + (r - n0) * p.hop;
             const float* raw = raw0 + (it & 1) * kRawFloats;
             PROF_START();
             mbar_wait_warp(bar_raw_full + 8 * (it & 1), (it >> 1) & 1);     // the unit's bulk copy has landed
             named_bar(2, kPreThreads);                           // ... and its edge samples; the other buffer is no longer read
             PROF_LAP(0);
             {
-                if (unit + ustride < total_units) {
-                    const UnitWalk nw = uw.peek();
-                    const long long g0 = nw.b * x_row_stride;
-                    stage_rest(x + g0, stage_geom(xbase4 + g0, nw.tu * kRows, min(kRows, p.frames - nw.tu * kRows), p),
-                               raw0 + ((it + 1) & 1) * kRawFloats, p.N, pt);
-                }
+                if (unit + ustride < total_units)
+                    stage_rest(x, xbase4, x_row_stride, uw.peek(), p, raw0 + ((it + 1) & 1) * kRawFloats, pt);
             }
             // the row is computed BEFORE the A tiles are claimed: this overlaps the previous unit's MMAs
             const bool live = active && r < valid;
             float P[7], Q[7];
             if (live) {
-                const float* fr = raw + aoff + r * p.hop;
+                const float* fr = raw + fr_off;
                 float pp[7], qq[7];
 #pragma unroll
                 for (int n1 = 0; n1 < 7; ++n1) {
@@ -511,11 +531,9 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
         const uint32_t a_hi = s_base + kOffAHi, a_lo = s_base + kOffALo;
         const uint32_t b0 = s_base + kOffB;
         const uint32_t raw_addr = s_base + kOffRaw;
-        UnitWalk lw(first_unit, ustride, p.units_per_row);       // walks two units ahead: the staging loads
-        auto load_unit = [&](int n) {                            // bulk copy of the CTA's n-th unit into buffer n & 1
-            const long long g0 = lw.b * x_row_stride;
-            stage_bulk(x + g0, stage_geom(xbase4 + g0, lw.tu * kRows, min(kRows, p.frames - lw.tu * kRows), p),
-                       raw_addr + (n & 1) * kRawFloats * 4, bar_raw_full + 8 * (n & 1));
+        UnitWalk lw(first_unit, ustride, p.frames);              // walks two units ahead: the staging loads
+        auto load_unit = [&](int n) {                            // bulk copies of the CTA's n-th unit into buffer n & 1
+            stage_bulk(x, xbase4, x_row_stride, lw, p, raw_addr + (n & 1) * kRawFloats * 4, bar_raw_full + 8 * (n & 1));
             lw.next();
         };
         if (first_unit < total_units) load_unit(0);
@@ -616,7 +634,8 @@ static int get_tables(int dev, float** out) {
 }  // namespace tc
 
 bool stft_tc511_supported(const float* x, int64_t N, int n_fft, int hop, const float* out) {
-    return n_fft == tc::kN && hop >= 1 && hop <= tc::kMaxHop && N > tc::kN / 2 &&
+    const int64_t frames = 1 + (N + 2 * (tc::kN / 2) - tc::kN) / (hop > 0 ? hop : 1);
+    return n_fft == tc::kN && hop >= 1 && hop <= tc::kMaxHop && N > tc::kN / 2 && frames >= tc::kRows &&   // a unit spans <= 2 signals
            (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 3) == 0;
 }
 
@@ -631,10 +650,10 @@ int stft_tc511_launch(const float* x, int64_t B, int64_t N, int64_t x_row_stride
     Params p;
     p.hop = hop; p.N = static_cast<int>(N); p.pad = kN / 2;
     p.frames = static_cast<int>(1 + (N + 2 * (kN / 2) - kN) / hop);
-    p.units_per_row = (p.frames + kRows - 1) / kRows;
-    p.total_units = B * static_cast<long long>(p.units_per_row);
-    if (p.total_units >= (1LL << 31) - 65536) return fail(AFD_ERR_UNSUPPORTED, "afd_stft_power: batch too large for one launch");
-    p.vec_ok = (reinterpret_cast<uintptr_t>(x) & 15) == 0 ? 1 : 0;
+    p.B = static_cast<int>(B);
+    p.total_rows = B * static_cast<long long>(p.frames);
+    p.total_units = (p.total_rows + kRows - 1) / kRows;
+    if (p.total_rows >= (1LL << 31) - (1 << 20) || B >= (1LL << 31) - 1) return fail(AFD_ERR_UNSUPPORTED, "afd_stft_power: batch too large for one launch");
     p.power = power; p.log_offset = log_offset; p.log_scale = log_scale ? 1 : 0; p.square = (power == 2.0f);
     p.normalize = ex.normalize; p.nmean = ex.nmean; p.nrstd = ex.nrstd; p.moments = ex.moments; p.store = out != nullptr;
     const bool ext = ex.normalize || ex.moments || !out;
