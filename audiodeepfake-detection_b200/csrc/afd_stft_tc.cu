@@ -45,10 +45,10 @@ namespace tc {
 
 constexpr int kN = 511;
 constexpr int kRows = 16;                     // STFT frames per unit
-constexpr int kEpiWarps = 8, kPreWarps = 19;
+constexpr int kEpiWarps = 8, kPreWarps = 10;
 constexpr int kEpiThreads = kEpiWarps * 32;   // 256
-constexpr int kPreThreads = kPreWarps * 32;   // 608: one (frame, m) item per thread, 592 used
-constexpr int kThreads = kEpiThreads + kPreThreads + 32;   // + MMA warp = 896
+constexpr int kPreThreads = kPreWarps * 32;   // 320: two (frame, m) items per thread (frames r, r + 8), 296 used
+constexpr int kThreads = kEpiThreads + kPreThreads + 32;   // + MMA warp = 608
 
 // A tile (bytes): 128 rows x 80 columns of fp32, K-major core matrices
 constexpr int kALbo = 144;                    // distance of consecutive 16-byte K chunks
@@ -230,9 +230,9 @@ __device__ __forceinline__ void stage_bulk(const float* __restrict__ x, long lon
     bulk_issue(x + g0, a, raw_addr, bar);
     if (n1 > 0) bulk_issue(x + g0 + stride, c, raw_addr + static_cast<uint32_t>(a.end - a.s_begin) * 4u, bar);
 }
-__device__ __forceinline__ void rest_one(const float* __restrict__ xrow, const StageGeom& g, float* __restrict__ raw, int N, int pt) {
+__device__ __forceinline__ void rest_one(const float* __restrict__ xrow, const StageGeom& g, float* __restrict__ raw, int N, int lane) {
     const int nlo = g.lo4 - g.s_begin, nhi = g.end - g.hi4;
-    for (int e = pt; e < nlo + nhi; e += kPreThreads) {
+    for (int e = lane; e < nlo + nhi; e += 32) {
         const int i = e < nlo ? e : (g.hi4 - g.s_begin) + (e - nlo);
         int sidx = g.s_begin + i;
         sidx = sidx < 0 ? -sidx : sidx;
@@ -241,14 +241,14 @@ __device__ __forceinline__ void rest_one(const float* __restrict__ xrow, const S
         raw[i] = __ldg(xrow + sidx);
     }
 }
-// The samples the bulk copies leave out (alignment slack, reflect padding).  All producer threads.
+// The samples the bulk copies leave out (alignment slack, reflect padding of a signal's first / last frames).  One warp.
 __device__ __forceinline__ void stage_rest(const float* __restrict__ x, long long xbase4, long long stride, const UnitWalk& w,
-                                           const Params& p, float* __restrict__ raw, int pt) {
+                                           const Params& p, float* __restrict__ raw, int lane) {
     const long long g0 = w.b * stride;
     const StageGeom a = stage_geom(xbase4 + g0, w.t, w.n0(), p);
-    rest_one(x + g0, a, raw, p.N, pt);
+    rest_one(x + g0, a, raw, p.N, lane);
     const int n1 = w.n1(p.B);
-    if (n1 > 0) rest_one(x + g0 + stride, stage_geom(xbase4 + g0 + stride, 0, n1, p), raw + (a.end - a.s_begin), p.N, pt);
+    if (n1 > 0) rest_one(x + g0 + stride, stage_geom(xbase4 + g0 + stride, 0, n1, p), raw + (a.end - a.s_begin), p.N, lane);
 }
 
 // MODE 0: power 2 + log (the reference's configuration), 1: power 2, linear, 2: any power / log flag (runtime)
@@ -378,7 +378,8 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
             const int buf = it & 1;
             float* const s_out = reinterpret_cast<float*>(smem + kOffOut) + buf * kOutFloats;
             PROF_START();
-            mbar_wait_warp(bar_d_full + 8 * buf, (it >> 1) & 1);
+            if (warp == 0) mbar_wait_warp(bar_d_full + 8 * buf, (it >> 1) & 1);   // one warp polls ...
+            named_bar(3, kEpiThreads);                           // ... the others park at a hardware barrier (no issue slots)
             PROF_LAP(0);
             tc_fence_after();
             const uint32_t taddr = lane_addr + buf * kDStride;
@@ -434,16 +435,18 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
             }
         }
     } else if (warp < kEpiWarps + kPreWarps) {
-        // ============================================================ producer warps: thread = (frame r, column m)
-        // warps 0..15: frame r = warp, m = lane (0..31): data, window and A-tile accesses of a warp walk along m and are
-        // bank-conflict free; warps 16..18: the remaining m = 32..36 of all 16 frames (80 items).
+        // ============================================================ producer warps: thread = (frames r0 and r0 + 8, column m)
+        // warps 0..7: r0 = warp, m = lane (0..31): data and A-tile accesses of a warp walk along m and are bank-conflict
+        // free; warps 8..9: the remaining m = 32..36 (40 threads).  Two independent frames per thread give the scheduler
+        // twice the instruction-level parallelism per warp; the window values of column m stay in registers.
         const int pt = tid - kEpiThreads;
         const int pw = pt >> 5;
-        const int pe = (pw - 16) * 32 + lane;
-        const bool active = pw < 16 || pe < 5 * kRows;
-        const int r = pw < 16 ? pw : (pe < 5 * kRows ? pe / 5 : 0);
-        const int pm = pw < 16 ? lane : (pe < 5 * kRows ? 32 + pe % 5 : 0);
+        const int pe = (pw - 8) * 32 + lane;
+        const bool active = pw < 8 || pe < 40;
+        const int r0 = pw < 8 ? pw : (pe < 40 ? pe / 5 : 0);
+        const int pm = pw < 8 ? lane : (pe < 40 ? 32 + pe % 5 : 0);
         int offA[7], offB[7];
+        float wA[7], wB[7];
 #pragma unroll
         for (int n1 = 0; n1 < 7; ++n1) {
             int a = 73 * n1 + 7 * pm;
@@ -452,75 +455,79 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
             bq = bq < 0 ? bq + kN : bq;
             offA[n1] = a;
             offB[n1] = bq;
+            wA[n1] = s_w[74 * n1 + pm];
+            wB[n1] = s_w[74 * n1 + 37 + pm];
         }
-        const float* const wA = s_w + pm;                      // [n1 * 74]: lanes walk along m -> conflict-free
-        const float* const wB = s_w + 37 + pm;
-        unsigned char* const arow = smem + kOffAHi + (pm >> 2) * kALbo + (pm & 3) * 4 + (r & 7) * 16 + (r >> 3) * kASbo;
+        unsigned char* const arow = smem + kOffAHi + (pm >> 2) * kALbo + (pm & 3) * 4 + r0 * 16;     // frame r0 + 8: + kASbo
         constexpr int kQ = 10 * kALbo;                                                      // column 40 + m
         float* const raw0 = reinterpret_cast<float*>(smem + kOffRaw);
         UnitWalk uw(first_unit, ustride, p.frames);
-        if (first_unit < total_units) stage_rest(x, xbase4, x_row_stride, uw, p, raw0, pt);
+        if (first_unit < total_units && pw == kPreWarps - 1) stage_rest(x, xbase4, x_row_stride, uw, p, raw0, lane);
         int it = 0;
         for (int unit = first_unit; unit < total_units; unit += ustride, ++it, uw.next()) {
             const int n0 = uw.n0();
             const int valid = n0 + uw.n1(p.B);
-            // where the thread's frame starts in the staging buffer: segment 0 (signal b) or segment 1 (signal b + 1)
+            // where the thread's frames start in the staging buffer: segment 0 (signal b) or segment 1 (signal b + 1)
             const int abs0 = static_cast<int>(xbase4 + uw.b * x_row_stride);
             const int aoff0 = (abs0 + (uw.t * p.hop - p.pad)) & 3;
             const int off1 = (aoff0 + (n0 - 1) * p.hop + kN + 3) & ~3;
             const int aoff1 = (abs0 + static_cast<int>(x_row_stride) - p.pad) & 3;
-            const int fr_off = r < n0 ? aoff0 + r * p.hop : off1 + aoff1 + (r - n0) * p.hop;
             const float* raw = raw0 + (it & 1) * kRawFloats;
             PROF_START();
             mbar_wait_warp(bar_raw_full + 8 * (it & 1), (it >> 1) & 1);     // the unit's bulk copy has landed
             named_bar(2, kPreThreads);                           // ... and its edge samples; the other buffer is no longer read
             PROF_LAP(0);
-            {
-                if (unit + ustride < total_units)
-                    stage_rest(x, xbase4, x_row_stride, uw.peek(), p, raw0 + ((it + 1) & 1) * kRawFloats, pt);
-            }
-            // the row is computed BEFORE the A tiles are claimed: this overlaps the previous unit's MMAs
-            const bool live = active && r < valid;
-            float P[7], Q[7];
-            if (live) {
-                const float* fr = raw + fr_off;
+            if (pw == kPreWarps - 1 && unit + ustride < total_units)     // the warp with the fewest items writes the edge samples
+                stage_rest(x, xbase4, x_row_stride, uw.peek(), p, raw0 + ((it + 1) & 1) * kRawFloats, lane);
+            // the frames are computed BEFORE the A tiles are claimed: this overlaps the previous unit's MMAs
+            float P[2][7], Q[2][7];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int r = r0 + 8 * rr;
+                // rows past the end of the batch (last unit only) read frame 0 of the buffer: finite values, never stored
+                const int fo = r < n0 ? aoff0 + r * p.hop : (r < valid ? off1 + aoff1 + (r - n0) * p.hop : 0);
+                const float* fr = raw + fo;
                 float pp[7], qq[7];
 #pragma unroll
                 for (int n1 = 0; n1 < 7; ++n1) {
-                    const float xa = fr[offA[n1]] * wA[74 * n1];
-                    const float xb = fr[offB[n1]] * wB[74 * n1];
+                    const float xa = fr[offA[n1]] * wA[n1];
+                    const float xb = fr[offB[n1]] * wB[n1];
                     pp[n1] = xa + xb;
                     qq[n1] = xa - xb;
                 }
-                dft7_real(pp, P);
-                dft7_real(qq, Q);
+                dft7_real(pp, P[rr]);
+                dft7_real(qq, Q[rr]);
             }
             PROF_LAP(1);
             if (it > 0) mbar_wait_warp(bar_p_free, (it - 1) & 1);     // the previous unit's Re MMAs have read the P block
             PROF_LAP(2);
-            if (live) {
 #pragma unroll
-                for (int s = 0; s < 7; ++s) {
-                    const int row8 = s == 0 ? 0 : 4 * ((s + 1) >> 1) + 2 * ((s + 1) & 1);   // (32 j + 16 h) / 8
-                    const float hi = __uint_as_float(__float_as_uint(P[s]) & 0xffffe000u);
-                    *reinterpret_cast<float*>(arow + row8 * kASbo) = hi;
-                    *reinterpret_cast<float*>(arow + row8 * kASbo + kATile) = P[s] - hi;
+            for (int rr = 0; rr < 2; ++rr)
+                if (active) {
+#pragma unroll
+                    for (int s = 0; s < 7; ++s) {
+                        const int row8 = (s == 0 ? 0 : 4 * ((s + 1) >> 1) + 2 * ((s + 1) & 1)) + rr;   // (32 j + 16 h) / 8 + frame / 8
+                        const float hi = __uint_as_float(__float_as_uint(P[rr][s]) & 0xffffe000u);
+                        *reinterpret_cast<float*>(arow + row8 * kASbo) = hi;
+                        *reinterpret_cast<float*>(arow + row8 * kASbo + kATile) = P[rr][s] - hi;
+                    }
                 }
-            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(bar_p_full);
             PROF_LAP(3);
             if (it > 0) mbar_wait_warp(bar_q_free, (it - 1) & 1);     // ... the Im MMAs the Q block
             PROF_LAP(4);
-            if (live && pm != 0) {
 #pragma unroll
-                for (int s = 0; s < 7; ++s) {
-                    const int row8 = s == 0 ? 0 : 4 * ((s + 1) >> 1) + 2 * ((s + 1) & 1);
-                    const float hi = __uint_as_float(__float_as_uint(Q[s]) & 0xffffe000u);
-                    *reinterpret_cast<float*>(arow + row8 * kASbo + kQ) = hi;
-                    *reinterpret_cast<float*>(arow + row8 * kASbo + kQ + kATile) = Q[s] - hi;
+            for (int rr = 0; rr < 2; ++rr)
+                if (active) {                                    // column 40 (m = 0) meets an all-zero table row: any finite value
+#pragma unroll
+                    for (int s = 0; s < 7; ++s) {
+                        const int row8 = (s == 0 ? 0 : 4 * ((s + 1) >> 1) + 2 * ((s + 1) & 1)) + rr;
+                        const float hi = __uint_as_float(__float_as_uint(Q[rr][s]) & 0xffffe000u);
+                        *reinterpret_cast<float*>(arow + row8 * kASbo + kQ) = hi;
+                        *reinterpret_cast<float*>(arow + row8 * kASbo + kQ + kATile) = Q[rr][s] - hi;
+                    }
                 }
-            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(bar_q_full);
             PROF_LAP(5);
