@@ -445,19 +445,19 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
         const bool active = pw < 8 || pe < 40;
         const int r0 = pw < 8 ? pw : (pe < 40 ? pe / 5 : 0);
         const int pm = pw < 8 ? lane : (pe < 40 ? 32 + pe % 5 : 0);
-        int offA[7], offB[7];
-        float wA[7], wB[7];
+        // Sample (n1, m) of a frame sits at offA[n1] = (73 n1 + 7 m) mod 511, its fold partner (n1, 73 - m) at
+        // (73 n1 - 7 m) mod 511 = 511 - offA[(7 - n1) mod 7], and the periodic Hann window is symmetric, so one offset and
+        // one window value per n1 serve both.  (m = 0: partner == sample, pp = 2 xa exactly; the table row m = 0 is 0.5.)
+        int offA[7];
+        float wA[7];
 #pragma unroll
         for (int n1 = 0; n1 < 7; ++n1) {
             int a = 73 * n1 + 7 * pm;
             a = a >= kN ? a - kN : a;
-            int bq = 73 * n1 - 7 * pm;
-            bq = bq < 0 ? bq + kN : bq;
             offA[n1] = a;
-            offB[n1] = bq;
             wA[n1] = s_w[74 * n1 + pm];
-            wB[n1] = s_w[74 * n1 + 37 + pm];
         }
+        const int wrap0 = pm == 0 ? 0 : kN;                    // (n1, m) = (0, 0) is its own partner at offset 0
         unsigned char* const arow = smem + kOffAHi + (pm >> 2) * kALbo + (pm & 3) * 4 + r0 * 16;     // frame r0 + 8: + kASbo
         constexpr int kQ = 10 * kALbo;                                                      // column 40 + m
         float* const raw0 = reinterpret_cast<float*>(smem + kOffRaw);
@@ -490,8 +490,9 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
                 float pp[7], qq[7];
 #pragma unroll
                 for (int n1 = 0; n1 < 7; ++n1) {
+                    const int nb = (7 - n1) % 7;
                     const float xa = fr[offA[n1]] * wA[n1];
-                    const float xb = fr[offB[n1]] * wB[n1];
+                    const float xb = fr[(n1 == 0 ? wrap0 : kN) - offA[nb]] * wA[nb];
                     pp[n1] = xa + xb;
                     qq[n1] = xa - xb;
                 }
@@ -608,7 +609,7 @@ static int get_tables(int dev, float** out) {
         if (m > 36 || k2 > 36) return 0.0;
         const int ph = (m * k2) % 73;                                    // exact phase reduction
         const double ang = 2.0 * M_PI * double(ph) / 73.0;
-        if (part == 0) return cos(ang);
+        if (part == 0) return m == 0 ? 0.5 : cos(ang);                   // the producers deliver 2 * p[., 0]
         return m == 0 ? 0.0 : -sin(ang);
     };
     for (int part = 0; part < 2; ++part)
