@@ -315,7 +315,7 @@ static int get_tables(int dev, int n, float2** out) {
 bool stft_pfa511_supported(const float* x, int64_t N, int n_fft, int hop, const float* out);
 int stft_pfa511_launch(const float* x, int64_t B, int64_t N, int64_t x_row_stride, int hop, float power, int log_scale,
                        float log_offset, const StftExtras& ex, float* out, cudaStream_t stream);
-bool stft_tc511_supported(const float* x, int64_t N, int n_fft, int hop, const float* out);
+bool stft_tc511_supported(const float* x, int64_t B, int64_t N, int n_fft, int hop, const float* out);
 int stft_tc511_launch(const float* x, int64_t B, int64_t N, int64_t x_row_stride, int hop, float power, int log_scale,
                       float log_offset, const StftExtras& ex, float* out, cudaStream_t stream);
 
@@ -348,7 +348,7 @@ static int stft_power_impl(const float* x, int64_t B, int64_t N, int64_t x_row_s
         const char* impl = getenv("AFD_STFT_IMPL");
         const bool force_generic = impl && strcmp(impl, "bluestein") == 0;
         const bool force_pfa = impl && strcmp(impl, "pfa") == 0;
-        if (!force_generic && !force_pfa && stft_tc511_supported(x, N, n_fft, hop, out))
+        if (!force_generic && !force_pfa && stft_tc511_supported(x, B, N, n_fft, hop, out))
             return stft_tc511_launch(x, B, N, x_row_stride, hop, power, log_scale, log_offset, ex, out,
                                      static_cast<cudaStream_t>(stream));
         if (!force_generic && stft_pfa511_supported(x, N, n_fft, hop, out))

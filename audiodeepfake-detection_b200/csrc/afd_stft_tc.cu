@@ -641,8 +641,9 @@ static int get_tables(int dev, float** out) {
 
 }  // namespace tc
 
-bool stft_tc511_supported(const float* x, int64_t N, int n_fft, int hop, const float* out) {
+bool stft_tc511_supported(const float* x, int64_t B, int64_t N, int n_fft, int hop, const float* out) {
     const int64_t frames = 1 + (N + 2 * (tc::kN / 2) - tc::kN) / (hop > 0 ? hop : 1);
+    if (B >= (1LL << 31) - 1 || B * frames >= (1LL << 31) - (1 << 20)) return false;      // 32-bit row / unit indices
     return n_fft == tc::kN && hop >= 1 && hop <= tc::kMaxHop && N > tc::kN / 2 && frames >= tc::kRows &&   // a unit spans <= 2 signals
            (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 3) == 0;
 }
