@@ -99,12 +99,15 @@ def _select(monkeypatch, impl):
 
 @pytest.mark.parametrize("impl", [None, "pfa"])
 @pytest.mark.parametrize("hop,N,B", [(220, 22050, 37), (100, 8000, 3), (242, 22050, 2), (1, 700, 2), (243, 22050, 2),
-                                     (220, 256, 3), (220, 3000, 17), (220, 22050, 300)])
+                                     (220, 256, 3), (220, 3000, 17), (220, 22050, 300), (220, 3520, 5), (137, 5000, 7),
+                                     (220, 22050, 1), (64, 1200, 9), (242, 4000, 3), (3, 600, 4), (220, 3521, 33)])
 def test_pfa511_tensor_core_path(hop, N, B, impl, cuda_device, monkeypatch):
     """n_fft = 511 takes the prime-factor / tensor-core kernels (hop <= 242; tcgen05 by default, mma.sync with
     AFD_STFT_IMPL=pfa): fp64 DFT parity, and agreement with the generic chirp-z kernel forced through
     AFD_STFT_IMPL=bluestein (hop 243 is served by the generic kernel anyway).  B = 300 gives every persistent CTA
-    several units (pipeline phases wrap)."""
+    several units (pipeline phases wrap); N = 3520 / 3521 give exactly 16 / 17 frames per signal (a unit of the tcgen05
+    kernel = 16 rows of the flattened (signal, frame) index, so units straddle signals at every phase); B = 1 ends in a
+    partial unit; fewer than 16 frames per signal (N = 256, 3000) is served by the mma.sync kernel."""
     rng = np.random.default_rng(hop * 7 + N)
     x = (rng.standard_normal((B, N)) * 0.1).astype(np.float32)
     want = ptwt_like.stft_power_explicit(torch.from_numpy(x).double().unsqueeze(1), 511, hop).numpy()
