@@ -443,8 +443,8 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
         const int pw = pt >> 5;
         const int pe = (pw - 8) * 32 + lane;
         const bool active = pw < 8 || pe < 40;
-        const int r0 = pw < 8 ? pw : (pe < 40 ? pe / 5 : 0);
-        const int pm = pw < 8 ? lane : (pe < 40 ? 32 + pe % 5 : 0);
+        const int r0 = pw < 8 ? pw : (pe < 40 ? pe & 7 : 0);            // frames fastest: banks 4 r0 + (m & 3) are distinct
+        const int pm = pw < 8 ? lane : (pe < 40 ? 32 + (pe >> 3) : 0);
         // Sample (n1, m) of a frame sits at offA[n1] = (73 n1 + 7 m) mod 511, its fold partner (n1, 73 - m) at
         // (73 n1 - 7 m) mod 511 = 511 - offA[(7 - n1) mod 7], and the periodic Hann window is symmetric, so one offset and
         // one window value per n1 serve both.  (m = 0: partner == sample, pp = 2 xa exactly; the table row m = 0 is 0.5.)
