@@ -107,6 +107,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (spin > (1u << 20)) __trap();       // a lost arrival must not hang the GPU
     }
 }
+// Knock-out timing builds (tools/stft_tc_knockout.py; results are wrong by construction, only the times matter):
+// 1 two of the 20 MMAs, 2 no epilogue math / tile stores, 3 no producer loads / DFT-7, 4 no A-tile stores, 5 no proxy fences,
+// 7 all of 1-4 (pipeline skeleton), 8 = 7 without the output row stores.
+#ifndef AFD_TC_KO
+#define AFD_TC_KO 0
+#endif
+#define AFD_KO(n) (AFD_TC_KO == (n) || ((n) <= 4 && AFD_TC_KO >= 7))
 #ifdef AFD_TC_PROF
 #define PROF_DECL() long long _pacc[6] = {0, 0, 0, 0, 0, 0}; long long _pt0 = 0
 #define PROF_START() _pt0 = clock64()
@@ -285,6 +292,7 @@ __device__ __forceinline__ void combine(uint32_t taddr, uint32_t bar_d_empty, fl
         for (int i = 0; i < 8; ++i) {
             const int k2 = col0 + i;
             if (k2 < kLo || k2 > kHi) continue;
+            if (AFD_KO(2) && k2 != kLo) continue;
             const float r = re[i] + re2[i], q = im[i] + im2[i];
             const float pre = __shfl_xor_sync(0xffffffffu, r, 16);
             const float pim = __shfl_xor_sync(0xffffffffu, q, 16);
@@ -393,7 +401,7 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
                 named_bar(1, kEpiThreads);                       // the unit's tile is complete; the other tile is free
                 PROF_LAP(2);
                 if (warp == 0 && lane < kRows) {
-                    if (lane < valid) {
+                    if (lane < valid && AFD_TC_KO != 8) {
                         float* og = out + (G0 + lane) * 256LL;
                         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 1024;"
                                      ::"l"(og), "r"(smem_u32(s_out + lane * kOutStride)) : "memory");
@@ -490,6 +498,7 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
                 float pp[7], qq[7];
 #pragma unroll
                 for (int n1 = 0; n1 < 7; ++n1) {
+                    if (AFD_KO(3)) { pp[n1] = fr[0]; qq[n1] = fr[1]; continue; }
                     const int nb = (7 - n1) % 7;
                     const float xa = fr[offA[n1]] * wA[n1];
                     const float xb = fr[(n1 == 0 ? wrap0 : kN) - offA[nb]] * wA[nb];
@@ -506,14 +515,14 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
             for (int rr = 0; rr < 2; ++rr)
                 if (active) {
 #pragma unroll
-                    for (int s = 0; s < 7; ++s) {
+                    for (int s = 0; s < (AFD_KO(4) ? 1 : 7); ++s) {
                         const int row8 = (s == 0 ? 0 : 4 * ((s + 1) >> 1) + 2 * ((s + 1) & 1)) + rr;   // (32 j + 16 h) / 8 + frame / 8
                         const float hi = __uint_as_float(__float_as_uint(P[rr][s]) & 0xffffe000u);
                         *reinterpret_cast<float*>(arow + row8 * kASbo) = hi;
                         *reinterpret_cast<float*>(arow + row8 * kASbo + kATile) = P[rr][s] - hi;
                     }
                 }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (!AFD_KO(5)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(bar_p_full);
             PROF_LAP(3);
             if (it > 0) mbar_wait_warp(bar_q_free, (it - 1) & 1);     // ... the Im MMAs the Q block
@@ -522,14 +531,14 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
             for (int rr = 0; rr < 2; ++rr)
                 if (active) {                                    // column 40 (m = 0) meets an all-zero table row: any finite value
 #pragma unroll
-                    for (int s = 0; s < 7; ++s) {
+                    for (int s = 0; s < (AFD_KO(4) ? 1 : 7); ++s) {
                         const int row8 = (s == 0 ? 0 : 4 * ((s + 1) >> 1) + 2 * ((s + 1) & 1)) + rr;
                         const float hi = __uint_as_float(__float_as_uint(Q[rr][s]) & 0xffffe000u);
                         *reinterpret_cast<float*>(arow + row8 * kASbo + kQ) = hi;
                         *reinterpret_cast<float*>(arow + row8 * kASbo + kQ + kATile) = Q[rr][s] - hi;
                     }
                 }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (!AFD_KO(5)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(bar_q_full);
             PROF_LAP(5);
         }
@@ -564,11 +573,11 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
                 const uint32_t bh = b0 + (2 * part) * kBTile;     // [hi tile | lo tile] = 96 rows of one N = 96 operand
                 const uint32_t ak = part * 10 * kALbo;
 #pragma unroll
-                for (int ks = 0; ks < 5; ++ks)                   // A_hi x [B_hi | B_lo] -> columns [0, 96)
+                for (int ks = 0; ks < (AFD_KO(1) ? 1 : 5); ++ks)     // A_hi x [B_hi | B_lo] -> columns [0, 96)
                     tc_mma_tf32(d, make_desc(a_hi + ak + 2 * ks * kALbo, kALbo, kASbo), make_desc(bh + 2 * ks * kBLbo, kBLbo, kBSbo),
                                 kIdesc96, ks != 0);
 #pragma unroll
-                for (int ks = 0; ks < 5; ++ks)                   // A_lo x B_hi -> columns [0, 48)
+                for (int ks = 0; ks < (AFD_KO(1) ? 0 : 5); ++ks)     // A_lo x B_hi -> columns [0, 48)
                     tc_mma_tf32(d, make_desc(a_lo + ak + 2 * ks * kALbo, kALbo, kASbo), make_desc(bh + 2 * ks * kBLbo, kBLbo, kBSbo),
                                 kIdesc48, 1);
                 tc_commit(part ? bar_q_free : bar_p_free);
