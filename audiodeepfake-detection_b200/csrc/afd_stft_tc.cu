@@ -22,7 +22,7 @@
 // Roles of the 16 warps of the one CTA per SM (each role walks the same unit sequence):
 //     warps 8..14  producers : stage the unit's samples (cp.async, next unit prefetched), window, fold, two 7-point real
 //                              DFTs per (frame, m), hi / lo split, store into the A tiles, arrive on `a_full`
-//     warp 15      MMA issuer: waits `a_full` (+ `d_empty` of the accumulator buffer), issues the 30 MMAs, commits to
+//     warp 18      MMA issuer: waits `a_full` (+ `d_empty` of the accumulator buffer), issues the 30 MMAs, commits to
 //                              `a_free` (producers may overwrite A) and `d_full` (accumulators ready)
 //     warps 0..7   epilogue  : warp w reads TMEM lanes 32 (w % 4) .. +31 (= j), half w / 4 of the k2 range;
 //                              tcgen05.ld, partner exchange (u <-> v sit 16 lanes apart), |Z|^2, log -> 16 x 256 tile in
@@ -60,6 +60,7 @@ constexpr int kBSbo = 10 * kBLbo;             // 1280
 constexpr int kBTile = 6 * kBSbo;             // 7680
 constexpr int kRawFloats = 4432;              // two segments: >= 14 * hop + 2 * (511 + 6)  (hop <= 242); one: 15 * hop + 517
 constexpr int kMaxHop = (kRawFloats - 2 * (kN + 6)) / (kRows - 2);
+constexpr int kRawBufs = 4;                   // staging depth: the bulk loads run kRawBufs units ahead of the producers
 constexpr int kOutStride = 260;               // floats per row of the output tile
 constexpr int kOutFloats = kRows * kOutStride;
 constexpr int kWFloats = 7 * 74;               // window, [n1][m] for the (n1, m) samples then [n1][37 + m] for (n1, 73 - m)
@@ -69,10 +70,10 @@ constexpr int kOffAHi = 0;
 constexpr int kOffALo = kOffAHi + kATile;
 constexpr int kOffB = kOffALo + kATile;                      // C hi, C lo, S hi, S lo
 constexpr int kOffRaw = kOffB + 4 * kBTile;                  // two staging buffers
-constexpr int kOffOut = kOffRaw + 2 * kRawFloats * 4;        // two output tiles
+constexpr int kOffOut = kOffRaw + kRawBufs * kRawFloats * 4;  // two output tiles
 constexpr int kOffW = kOffOut + 2 * kOutFloats * 4;
 constexpr int kOffBar = kOffW + kWFloats * 4;                // mbarriers + TMEM base address
-constexpr int kSmemBytes = kOffBar + 128;
+constexpr int kSmemBytes = kOffBar + 128 + 8 * kRawBufs;
 constexpr int kTableFloats = 4 * kBTile / 4 + kWFloats;      // device table: B tiles (byte-exact smem image) + window
 
 constexpr int kTmemCols = 512;
@@ -318,7 +319,7 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
     const uint32_t bar_p_free = bar_p_full + 16, bar_q_free = bar_p_full + 24;
     const uint32_t bar_d_full = bar_p_full + 32, bar_d_empty = bar_p_full + 48;      // two each
     uint32_t* const s_tmem = reinterpret_cast<uint32_t*>(smem + kOffBar + 64);
-    const uint32_t bar_raw_full = bar_p_full + 80;                                     // two: bulk copies of the staging buffers
+    const uint32_t bar_raw_full = bar_p_full + 128;                                    // kRawBufs: bulk copies of the staging buffers
 
     // ---- one-time setup: tables -> shared memory, A tiles zeroed, barriers, tensor memory
     {
@@ -329,7 +330,7 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
         float4* a = reinterpret_cast<float4*>(smem + kOffAHi);
         for (int i = tid; i < 2 * kATile / 16; i += kThreads) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         float4* o = reinterpret_cast<float4*>(smem + kOffRaw);
-        for (int i = tid; i < (2 * kRawFloats + 2 * kOutFloats) / 4; i += kThreads) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < (kRawBufs * kRawFloats + 2 * kOutFloats) / 4; i += kThreads) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (tid == 0) {
         mbar_init(bar_p_full, kPreThreads);
@@ -340,8 +341,7 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
         mbar_init(bar_d_full + 8, 1);
         mbar_init(bar_d_empty, kEpiThreads);
         mbar_init(bar_d_empty + 8, kEpiThreads);
-        mbar_init(bar_raw_full, 1);
-        mbar_init(bar_raw_full + 8, 1);
+        for (int i = 0; i < kRawBufs; ++i) mbar_init(bar_raw_full + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kThreads / 32 - 1) {
@@ -480,13 +480,13 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
             const int aoff0 = (abs0 + (uw.t * p.hop - p.pad)) & 3;
             const int off1 = (aoff0 + (n0 - 1) * p.hop + kN + 3) & ~3;
             const int aoff1 = (abs0 + static_cast<int>(x_row_stride) - p.pad) & 3;
-            const float* raw = raw0 + (it & 1) * kRawFloats;
+            const float* raw = raw0 + (it % kRawBufs) * kRawFloats;
             PROF_START();
-            mbar_wait_warp(bar_raw_full + 8 * (it & 1), (it >> 1) & 1);     // the unit's bulk copy has landed
+            mbar_wait_warp(bar_raw_full + 8 * (it % kRawBufs), (it / kRawBufs) & 1);     // the unit's bulk copy has landed
             named_bar(2, kPreThreads);                           // ... and its edge samples; the other buffer is no longer read
             PROF_LAP(0);
             if (pw == kPreWarps - 1 && unit + ustride < total_units)     // the warp with the fewest items writes the edge samples
-                stage_rest(x, xbase4, x_row_stride, uw.peek(), p, raw0 + ((it + 1) & 1) * kRawFloats, lane);
+                stage_rest(x, xbase4, x_row_stride, uw.peek(), p, raw0 + ((it + 1) % kRawBufs) * kRawFloats, lane);
             // the frames are computed BEFORE the A tiles are claimed: this overlaps the previous unit's MMAs
             float P[2][7], Q[2][7];
 #pragma unroll
@@ -550,11 +550,11 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
         const uint32_t raw_addr = s_base + kOffRaw;
         UnitWalk lw(first_unit, ustride, p.frames);              // walks two units ahead: the staging loads
         auto load_unit = [&](int n) {                            // bulk copies of the CTA's n-th unit into buffer n & 1
-            stage_bulk(x, xbase4, x_row_stride, lw, p, raw_addr + (n & 1) * kRawFloats * 4, bar_raw_full + 8 * (n & 1));
+            stage_bulk(x, xbase4, x_row_stride, lw, p, raw_addr + (n % kRawBufs) * kRawFloats * 4, bar_raw_full + 8 * (n % kRawBufs));
             lw.next();
         };
-        if (first_unit < total_units) load_unit(0);
-        if (first_unit + ustride < total_units) load_unit(1);
+        for (int n = 0; n < kRawBufs; ++n)
+            if (static_cast<long long>(first_unit) + static_cast<long long>(n) * ustride < total_units) load_unit(n);
         int it = 0;
         for (int unit = first_unit; unit < total_units; unit += ustride, ++it) {
             const int buf = it & 1;
@@ -562,11 +562,7 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
             for (int part = 0; part < 2; ++part) {               // 0: Re = P x C, 1: Im = Q x S
                 PROF_START();
                 mbar_wait(part ? bar_q_full : bar_p_full, it & 1);
-                if (part == 0) {
-                    // p_full(it): every producer has finished reading staging buffer it & 1 -> refill it for unit it + 2
-                    if (static_cast<long long>(unit) + 2LL * ustride < total_units) load_unit(it + 2);
-                    if (it >= 2) mbar_wait(bar_d_empty + 8 * buf, ((it >> 1) - 1) & 1);
-                }
+                if (part == 0 && it >= 2) mbar_wait(bar_d_empty + 8 * buf, ((it >> 1) - 1) & 1);
                 PROF_LAP(2 * part);
                 tc_fence_after();
                 const uint32_t d = tmem_base + buf * kDStride + part * 96;
@@ -581,6 +577,10 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
                     tc_mma_tf32(d, make_desc(a_lo + ak + 2 * ks * kALbo, kALbo, kASbo), make_desc(bh + 2 * ks * kBLbo, kBLbo, kBSbo),
                                 kIdesc48, 1);
                 tc_commit(part ? bar_q_free : bar_p_free);
+                // p_full(it) has completed: every producer has finished reading staging buffer it % kRawBufs -> refill it
+                // (after the MMAs are issued: the address arithmetic of the bulk copies stays off the A-tile round trip)
+                if (part == 0 && static_cast<long long>(unit) + static_cast<long long>(kRawBufs) * ustride < total_units)
+                    load_unit(it + kRawBufs);
                 if (part == 1) tc_commit(bar_d_full + 8 * buf);
                 PROF_LAP(2 * part + 1);
             }
