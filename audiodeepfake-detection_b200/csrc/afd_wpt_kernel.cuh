@@ -225,6 +225,9 @@ __device__ __forceinline__ void lattice2(float (&w)[WLEN], const Coefs<F>& cf, f
 #define AFD_WPT_FFMA2 1
 #endif
 constexpr int kPackedMaxF = 16;
+#ifndef AFD_WPT_PACKED_FIR_MAXF
+#define AFD_WPT_PACKED_FIR_MAXF 32   // level-1 direct form: packed for F <= this (coif4: 1 % faster, same-box A/B); lattice: kPackedMaxF
+#endif
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk2(float lo, float hi) {
     u64 r;
@@ -504,7 +507,7 @@ __device__ __forceinline__ void level1_chunk(const float* __restrict__ buf, floa
         float w[WN::WLEN];
         load_window<WN::NV>(buf + 2 * i * R, w);
         float y[R];
-        if constexpr (AFD_WPT_FFMA2 != 0 && F <= kPackedMaxF) fir1_packed<F, R>(w, t2, y);
+        if constexpr (AFD_WPT_FFMA2 != 0 && F <= AFD_WPT_PACKED_FIR_MAXF) fir1_packed<F, R>(w, t2, y);
         else fir1<F, R>(w, t, y);
         if (c >= sp.CL && c < sp.CIe) vec_store<R>(node + padl + k0, y);
         else edge_store<R>(node, y, k0, n_out, padl);
