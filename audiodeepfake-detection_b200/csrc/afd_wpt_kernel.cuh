@@ -225,6 +225,21 @@ __device__ __forceinline__ void lattice2(float (&w)[WLEN], const Coefs<F>& cf, f
 #define AFD_WPT_FFMA2 1
 #endif
 constexpr int kPackedMaxF = 16;
+// Left reflect padding without stores (r1d): the only reader of a node's left padding is the consumer chunk 0 of the
+// next level (when every item size R >= F/2), and for that chunk the reflection x~[-i] = x[i] is a COMPILE-TIME
+// permutation of its own register window (w[j] = w[2F-4-j], j < F-2).  So the producers skip the left mirror stores
+// (lanes across nodes: 8-way bank conflicts, F-2 scalar stores per channel) and chunk 0 fixes its window up in registers.
+// The right padding is still materialised: its reflection point depends on the node length (run time).
+#ifndef AFD_WPT_REFLECT_REGS
+#define AFD_WPT_REFLECT_REGS 1
+#endif
+template <int F, int... Rs>
+struct ReflOk {
+    static constexpr bool value = AFD_WPT_REFLECT_REGS && ((Rs >= F / 2) && ...);
+};
+#ifndef AFD_WPT_KO_MIRRORS
+#define AFD_WPT_KO_MIRRORS 0      // knock-out timing: 1 skips the mirror (padding) stores of the edge items -- wrong results
+#endif
 #ifndef AFD_WPT_PACKED_FIR_MAXF
 #define AFD_WPT_PACKED_FIR_MAXF 32   // level-1 direct form: packed for F <= this (coif4: 1 % faster, same-box A/B); lattice: kPackedMaxF
 #endif
@@ -336,12 +351,18 @@ __device__ __forceinline__ void load_window(const float* __restrict__ p, float (
     }
 }
 
-template <int F, int R, bool LAT>
+template <int F, int R, bool LAT, bool REFL>
 __device__ __forceinline__ void filter_pair(const float* __restrict__ src, const Coefs<F>& cf, float (&lo)[R],
-                                            float (&hi)[R]) {
+                                            float (&hi)[R], bool first) {
     using WN = Win<F, R>;
     float w[WN::WLEN];
     load_window<WN::NV>(src, w);
+    if constexpr (REFL) {
+        if (first) {                       // chunk 0: the left padding is the mirror image of the window's own samples
+#pragma unroll
+            for (int j = 0; j < F - 2; ++j) w[j] = w[2 * F - 4 - j];
+        }
+    }
     if constexpr (LAT && AFD_WPT_FFMA2 && F >= 6 && F <= kPackedMaxF) lattice2_packed<F, R>(w, cf, lo, hi);
     else if constexpr (LAT) lattice2<F, R>(w, cf, lo, hi);
     else fir2<F, R>(w, cf, lo, hi);
@@ -382,7 +403,7 @@ __device__ __forceinline__ void vec_store(float* __restrict__ dst, const float (
 
 // Generic guarded store of R coefficients of a child node plus their mirror images into the node's padding.
 // `node` points at the first padding sample; coefficient k lives at node[padl + k].
-template <int R>
+template <int R, bool REFL>
 __device__ __forceinline__ void edge_store(float* __restrict__ node, const float (&v)[R], int k0, int n_out, int padl) {
     const int padr = padl + (n_out & 1);
     float* pos = node + padl;
@@ -391,15 +412,15 @@ __device__ __forceinline__ void edge_store(float* __restrict__ node, const float
         const int k = k0 + r;
         if (k < n_out) {
             pos[k] = v[r];
-            if (k >= 1 && k <= padl) pos[-k] = v[r];
+            if (!REFL && !AFD_WPT_KO_MIRRORS && k >= 1 && k <= padl) pos[-k] = v[r];
             const int mr = n_out - 1 - k;
-            if (mr >= 1 && mr <= padr) pos[n_out - 1 + mr] = v[r];
+            if (!AFD_WPT_KO_MIRRORS && mr >= 1 && mr <= padr) pos[n_out - 1 + mr] = v[r];
         }
     }
 }
 
 // Left-edge chunk C (compile time) of a pair of sibling nodes: fully valid, mirrors k = 1 .. padl to -k.
-template <int R, int PADL, int C>
+template <int R, int PADL, int C, bool REFL>
 __device__ __forceinline__ void left_store(float* __restrict__ plo, float* __restrict__ phi, const float (&lo)[R],
                                            const float (&hi)[R]) {
     vec_store<R>(plo + C * R, lo);
@@ -407,7 +428,7 @@ __device__ __forceinline__ void left_store(float* __restrict__ plo, float* __res
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int k = C * R + r;
-        if (k >= 1 && k <= PADL) {
+        if (!REFL && !AFD_WPT_KO_MIRRORS && k >= 1 && k <= PADL) {
             plo[-k] = lo[r];
             phi[-k] = hi[r];
         }
@@ -436,7 +457,7 @@ __device__ __forceinline__ void right_store(float* __restrict__ plo, float* __re
     }
 #pragma unroll
     for (int r = 0; r < R; ++r)
-        if (static_cast<unsigned>(q - r - 1) < static_cast<unsigned>(padr)) { mlo[-r] = lo[r]; mhi[-r] = hi[r]; }
+        if (!AFD_WPT_KO_MIRRORS && static_cast<unsigned>(q - r - 1) < static_cast<unsigned>(padr)) { mlo[-r] = lo[r]; mhi[-r] = hi[r]; }
 }
 
 template <int R>
@@ -447,7 +468,7 @@ __device__ __forceinline__ void scale_all(float (&lo)[R], float (&hi)[R], float 
 
 // One stored tree level: `parents` padded nodes in `in` -> 2*parents padded nodes in `out`.
 // Interior chunks first (lanes walk along a node), then the edge chunks type-major (lanes walk across nodes).
-template <int F, int R, bool LAT>
+template <int F, int R, bool LAT, bool REFL>
 __device__ __forceinline__ void mid_level(const float* __restrict__ in, float* __restrict__ out, const Pass& ps,
                                           const Coefs<F>& cf) {
     constexpr int padl = F - 2;
@@ -472,7 +493,7 @@ __device__ __forceinline__ void mid_level(const float* __restrict__ in, float* _
         }
         const int k0 = c * R;
         float lo[R], hi[R];
-        filter_pair<F, R, LAT>(in + node * ps.in_stride + 2 * k0, cf, lo, hi);
+        filter_pair<F, R, LAT, REFL>(in + node * ps.in_stride + 2 * k0, cf, lo, hi, c == 0);
         if (do_mul) scale_all<R>(lo, hi, ps.mul);
         float* d0 = out + (2 * node) * ps.out_stride;
         float* d1 = d0 + ps.out_stride;
@@ -481,12 +502,12 @@ __device__ __forceinline__ void mid_level(const float* __restrict__ in, float* _
             vec_store<R>(d1 + padl + k0, hi);
         } else {
             const bool left = c < sp.CL, right = c >= sp.CR;
-            if (left && !right && c == 0) left_store<R, padl, 0>(d0 + padl, d1 + padl, lo, hi);
-            else if (left && !right && c == 1) left_store<R, padl, 1>(d0 + padl, d1 + padl, lo, hi);
+            if (left && !right && c == 0) left_store<R, padl, 0, REFL>(d0 + padl, d1 + padl, lo, hi);
+            else if (left && !right && c == 1) left_store<R, padl, 1, REFL>(d0 + padl, d1 + padl, lo, hi);
             else if (right && !left) right_store<R>(d0 + padl, d1 + padl, lo, hi, k0, n_out, padl);
             else {
-                edge_store<R>(d0, lo, k0, n_out, padl);
-                edge_store<R>(d1, hi, k0, n_out, padl);
+                edge_store<R, REFL>(d0, lo, k0, n_out, padl);
+                edge_store<R, REFL>(d1, hi, k0, n_out, padl);
             }
         }
     }
@@ -494,7 +515,7 @@ __device__ __forceinline__ void mid_level(const float* __restrict__ in, float* _
 
 // Level 1 for one staged chunk: outputs [kb, ke) of the CTA's own filter -> padded level-1 node.
 // Sample 2*kb + 2 - F of the (reflect-extended) frame sits at buf[0].
-template <int F, int R>
+template <int F, int R, bool REFL>
 __device__ __forceinline__ void level1_chunk(const float* __restrict__ buf, float* __restrict__ node, int kb, int ke,
                                              int n_out, const Split& sp, const float (&t)[F], const u64 (&t2)[F / 2]) {
     using WN = Win<F, R>;
@@ -510,7 +531,7 @@ __device__ __forceinline__ void level1_chunk(const float* __restrict__ buf, floa
         if constexpr (AFD_WPT_FFMA2 != 0 && F <= AFD_WPT_PACKED_FIR_MAXF) fir1_packed<F, R>(w, t2, y);
         else fir1<F, R>(w, t, y);
         if (c >= sp.CL && c < sp.CIe) vec_store<R>(node + padl + k0, y);
-        else edge_store<R>(node, y, k0, n_out, padl);
+        else edge_store<R, REFL>(node, y, k0, n_out, padl);
     }
 }
 // Chunks are cut at multiples of R, so only the last chunk (ke == n_out) holds a partial item.
@@ -521,7 +542,7 @@ __device__ __forceinline__ unsigned igray(unsigned x) {
 }
 
 // Last level: `parents` padded nodes (level L-1) -> features in global memory.  Lanes map to parents.
-template <int F, int RL, bool LAT, bool EXT>
+template <int F, int RL, bool LAT, bool EXT, bool REFL>
 __device__ __forceinline__ void last_level(const float* __restrict__ in, const Pass& ps, int T, int half_base,
                                            float* __restrict__ out_b, int P, const Coefs<F>& cf, const Epilogue& ep,
                                            ThreadStats& ts) {
@@ -539,7 +560,7 @@ __device__ __forceinline__ void last_level(const float* __restrict__ in, const P
         const int c = it >> ps.lg_parents;
         const int k0 = c * RL;
         float lo[RL], hi[RL];
-        filter_pair<F, RL, LAT>(in + m * ps.in_stride + 2 * k0, cf, lo, hi);
+        filter_pair<F, RL, LAT, REFL>(in + m * ps.in_stride + 2 * k0, cf, lo, hi, c == 0);
         if (do_mul) scale_all<RL>(lo, hi, ps.mul);
         const unsigned pf = static_cast<unsigned>(half_base + ps.parent_base + m);      // natural index at level L-1
         unsigned q = pf;
@@ -670,6 +691,7 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
                 const __grid_constant__ Epilogue ep) {
     extern __shared__ __align__(16) float smem[];
     constexpr int padl = F - 2;
+    constexpr bool REFL = ReflOk<F, RA, RB, RLA, RLB>::value;      // left padding by register reflection (see ReflOk)
     const int L = plan.L;
     const int half = blockIdx.x & 1;                      // gridDim.x is even: constant per CTA
     float* const regA = smem;                              // level-1 node at its start
@@ -713,7 +735,7 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
             if (j + 1 < plan.nch) issue_chunk<F>(xg, ((j + 1) & 1) ? buf1 : buf0, j + 1, plan);
             const int kb = j * plan.kc;
             const int ke = min(n1, kb + plan.kc);
-            level1_chunk<F, R1>((j & 1) ? buf1 : buf0, regA, kb, ke, n1, sp1, t1, t1p);
+            level1_chunk<F, R1, REFL>((j & 1) ? buf1 : buf0, regA, kb, ke, n1, sp1, t1, t1p);
         }
         __syncthreads();
         float* out_b = out + b * C * static_cast<long long>(T) * P;
@@ -746,16 +768,16 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
             const Pass& ps = plan.pass[pi];
             if (ps.sync_before) __syncthreads();
             if (ps.kind == 0) {
-                if (ps.rsel == 0) mid_level<F, RA, LAT>(smem + ps.in_off, smem + ps.out_off, ps, cf);
-                else mid_level<F, RB, LAT>(smem + ps.in_off, smem + ps.out_off, ps, cf);
+                if (ps.rsel == 0) mid_level<F, RA, LAT, REFL>(smem + ps.in_off, smem + ps.out_off, ps, cf);
+                else mid_level<F, RB, LAT, REFL>(smem + ps.in_off, smem + ps.out_off, ps, cf);
                 __syncthreads();
             } else {
                 if (ps.prefetch && nb < 2 * B) {
                     issue_chunk<F>(x + (nb >> 1) * x_row_stride, buf0, 0, plan);
                     prefetched = true;
                 }
-                if (ps.rsel == 0) last_level<F, RLA, LAT, EXT>(smem + ps.in_off, ps, T, half_base, out_b, P, cf, ep, ts);
-                else last_level<F, RLB, LAT, EXT>(smem + ps.in_off, ps, T, half_base, out_b, P, cf, ep, ts);
+                if (ps.rsel == 0) last_level<F, RLA, LAT, EXT, REFL>(smem + ps.in_off, ps, T, half_base, out_b, P, cf, ep, ts);
+                else last_level<F, RLB, LAT, EXT, REFL>(smem + ps.in_off, ps, T, half_base, out_b, P, cf, ep, ts);
             }
         }
     }
