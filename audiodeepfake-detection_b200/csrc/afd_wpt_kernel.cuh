@@ -60,6 +60,7 @@ struct Pass {
     int rsel;          // which of the two item sizes
     float mul;         // factor folded into the stores (1: none)
     int parent_base;   // natural index (within the half tree) of the first parent, last level only
+    int n_in;          // parent node length
     int prefetch;      // the next frame's first chunk may be staged while this pass runs
     int sync_before;   // barrier needed before this pass even if the previous pass ended with one
     // chunk classification of the child nodes for the chosen item size (make_split, evaluated on the host)
@@ -237,6 +238,14 @@ template <int F, int... Rs>
 struct ReflOk {
     static constexpr bool value = AFD_WPT_REFLECT_REGS && ((Rs >= F / 2) && ...);
 };
+// Right padding (AFD_WPT_REFLECT_RIGHT, off): its reflection point is the node length, known only at run time, so the
+// chunks whose window crosses the node's end would re-read the mirrored samples with predicated scalar loads
+// (w[j] = src[2 jn - j], jn = window index of the node's last sample) instead of the producers storing them.  Measured
+// (same-box A/B, bit-identical): coif4 +20 % time, sym5 +1.5 % -- ~70 predicated loads per edge item cost more than the
+// F-1 conflicted stores they replace -- so the right padding stays materialised.
+#ifndef AFD_WPT_REFLECT_RIGHT
+#define AFD_WPT_REFLECT_RIGHT 0
+#endif
 #ifndef AFD_WPT_KO_MIRRORS
 #define AFD_WPT_KO_MIRRORS 0      // knock-out timing: 1 skips the mirror (padding) stores of the edge items -- wrong results
 #endif
@@ -353,10 +362,18 @@ __device__ __forceinline__ void load_window(const float* __restrict__ p, float (
 
 template <int F, int R, bool LAT, bool REFL>
 __device__ __forceinline__ void filter_pair(const float* __restrict__ src, const Coefs<F>& cf, float (&lo)[R],
-                                            float (&hi)[R], bool first) {
+                                            float (&hi)[R], bool first, int jn) {
     using WN = Win<F, R>;
     float w[WN::WLEN];
     load_window<WN::NV>(src, w);
+    if constexpr (REFL && AFD_WPT_REFLECT_RIGHT) {
+        if (jn < WN::W - 1) {              // the window crosses the node's end: x~[n-1+i] = x[n-1-i], i = 1 .. F-2 (+1)
+            const unsigned padr = static_cast<unsigned>(F - 2 + ((jn + 1) & 1));     // jn = n + F - 3 - 2 k0: n odd <=> jn even
+#pragma unroll
+            for (int j = 1; j < WN::W; ++j)
+                if (static_cast<unsigned>(j - jn - 1) < padr) w[j] = src[2 * jn - j];
+        }
+    }
     if constexpr (REFL) {
         if (first) {                       // chunk 0: the left padding is the mirror image of the window's own samples
 #pragma unroll
@@ -414,7 +431,7 @@ __device__ __forceinline__ void edge_store(float* __restrict__ node, const float
             pos[k] = v[r];
             if (!REFL && !AFD_WPT_KO_MIRRORS && k >= 1 && k <= padl) pos[-k] = v[r];
             const int mr = n_out - 1 - k;
-            if (!AFD_WPT_KO_MIRRORS && mr >= 1 && mr <= padr) pos[n_out - 1 + mr] = v[r];
+            if (!(REFL && AFD_WPT_REFLECT_RIGHT) && !AFD_WPT_KO_MIRRORS && mr >= 1 && mr <= padr) pos[n_out - 1 + mr] = v[r];
         }
     }
 }
@@ -438,7 +455,7 @@ __device__ __forceinline__ void left_store(float* __restrict__ plo, float* __res
 // Right-edge chunk of a pair of sibling nodes (no left-mirrored coefficient inside): outputs k0+r are valid for
 // r <= q = n_out-1-k0 and mirrored to n_out-1+mr (mr = q - r) for 1 <= mr <= padr; one predicate pair serves both
 // channels.  plo / phi point at coefficient 0.
-template <int R>
+template <int R, bool REFL>
 __device__ __forceinline__ void right_store(float* __restrict__ plo, float* __restrict__ phi, const float (&lo)[R],
                                             const float (&hi)[R], int k0, int n_out, int padl) {
     const int padr = padl + (n_out & 1);
@@ -457,7 +474,7 @@ __device__ __forceinline__ void right_store(float* __restrict__ plo, float* __re
     }
 #pragma unroll
     for (int r = 0; r < R; ++r)
-        if (!AFD_WPT_KO_MIRRORS && static_cast<unsigned>(q - r - 1) < static_cast<unsigned>(padr)) { mlo[-r] = lo[r]; mhi[-r] = hi[r]; }
+        if (!(REFL && AFD_WPT_REFLECT_RIGHT) && !AFD_WPT_KO_MIRRORS && static_cast<unsigned>(q - r - 1) < static_cast<unsigned>(padr)) { mlo[-r] = lo[r]; mhi[-r] = hi[r]; }
 }
 
 template <int R>
@@ -493,7 +510,7 @@ __device__ __forceinline__ void mid_level(const float* __restrict__ in, float* _
         }
         const int k0 = c * R;
         float lo[R], hi[R];
-        filter_pair<F, R, LAT, REFL>(in + node * ps.in_stride + 2 * k0, cf, lo, hi, c == 0);
+        filter_pair<F, R, LAT, REFL>(in + node * ps.in_stride + 2 * k0, cf, lo, hi, c == 0, ps.n_in + F - 3 - 2 * k0);
         if (do_mul) scale_all<R>(lo, hi, ps.mul);
         float* d0 = out + (2 * node) * ps.out_stride;
         float* d1 = d0 + ps.out_stride;
@@ -504,7 +521,7 @@ __device__ __forceinline__ void mid_level(const float* __restrict__ in, float* _
             const bool left = c < sp.CL, right = c >= sp.CR;
             if (left && !right && c == 0) left_store<R, padl, 0, REFL>(d0 + padl, d1 + padl, lo, hi);
             else if (left && !right && c == 1) left_store<R, padl, 1, REFL>(d0 + padl, d1 + padl, lo, hi);
-            else if (right && !left) right_store<R>(d0 + padl, d1 + padl, lo, hi, k0, n_out, padl);
+            else if (right && !left) right_store<R, REFL>(d0 + padl, d1 + padl, lo, hi, k0, n_out, padl);
             else {
                 edge_store<R, REFL>(d0, lo, k0, n_out, padl);
                 edge_store<R, REFL>(d1, hi, k0, n_out, padl);
@@ -560,7 +577,7 @@ __device__ __forceinline__ void last_level(const float* __restrict__ in, const P
         const int c = it >> ps.lg_parents;
         const int k0 = c * RL;
         float lo[RL], hi[RL];
-        filter_pair<F, RL, LAT, REFL>(in + m * ps.in_stride + 2 * k0, cf, lo, hi, c == 0);
+        filter_pair<F, RL, LAT, REFL>(in + m * ps.in_stride + 2 * k0, cf, lo, hi, c == 0, ps.n_in + F - 3 - 2 * k0);
         if (do_mul) scale_all<RL>(lo, hi, ps.mul);
         const unsigned pf = static_cast<unsigned>(half_base + ps.parent_base + m);      // natural index at level L-1
         unsigned q = pf;
@@ -880,7 +897,7 @@ static int make_plan(int64_t N, int F, int L, const Tuning& tu, int ctas_per_sm,
         Pass& ps = p->pass[np++];
         ps = Pass{};
         ps.kind = 0; ps.in_off = region(l - 1); ps.out_off = region(l);
-        ps.parents = 1 << (l - 2); ps.lg_parents = l - 2; ps.n_out = n[l];
+        ps.parents = 1 << (l - 2); ps.lg_parents = l - 2; ps.n_out = n[l]; ps.n_in = n[l - 1];
         ps.in_stride = stride[l - 1]; ps.out_stride = stride[l];
         ps.rsel = pick(ps.parents, ps.n_out, tu.RA, tu.RB);
         ps.mul = stored_mul();
@@ -898,7 +915,7 @@ static int make_plan(int64_t N, int F, int L, const Tuning& tu, int ctas_per_sm,
             ps = Pass{};
             const int par = per_group / 2;                    // level L-2 parents of this slice
             ps.kind = 0; ps.in_off = region(L - 2) + g * par * stride[L - 2]; ps.out_off = region(L - 1);
-            ps.parents = par; ps.lg_parents = ilog2(par); ps.n_out = n[L - 1];
+            ps.parents = par; ps.lg_parents = ilog2(par); ps.n_out = n[L - 1]; ps.n_in = n[L - 2];
             ps.in_stride = stride[L - 2]; ps.out_stride = stride[L - 1];
             ps.rsel = pick(par, ps.n_out, tu.RA, tu.RB);
             ps.mul = grouped_mul;
@@ -908,7 +925,7 @@ static int make_plan(int64_t N, int F, int L, const Tuning& tu, int ctas_per_sm,
         Pass& ps = p->pass[np++];
         ps = Pass{};
         ps.kind = 1; ps.in_off = region(L - 1);
-        ps.parents = per_group; ps.lg_parents = ilog2(per_group); ps.n_out = n[L];
+        ps.parents = per_group; ps.lg_parents = ilog2(per_group); ps.n_out = n[L]; ps.n_in = n[L - 1];
         ps.in_stride = stride[L - 1];
         ps.rsel = pick(per_group, n[L], tu.RLA, tu.RLB);
         ps.mul = last_mul;
