@@ -1,3 +1,7 @@
+"""Per-role clock64 breakdown of the tcgen05 STFT kernel (one CTA prints its averages per unit).
+Build the instrumented library first (CPU, nvcc only):
+  python -c "import importlib.util as u; s=u.spec_from_file_location('b','audiodeepfake-detection_b200/build.py'); m=u.module_from_spec(s); s.loader.exec_module(m); m.build(True, extra_flags=['-DAFD_TC_PROF'], out_path=m.PKG_DIR+'/libafd_b200_prof.so')"
+then run this script on the GPU box."""
 import ctypes, os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = ctypes.CDLL(os.path.join(ROOT, "audiodeepfake-detection_b200", "libafd_b200_prof.so"))
