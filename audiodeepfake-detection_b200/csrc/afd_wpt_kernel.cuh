@@ -246,6 +246,12 @@ struct ReflOk {
 #ifndef AFD_WPT_REFLECT_RIGHT
 #define AFD_WPT_REFLECT_RIGHT 0
 #endif
+// Right padding by a copy pass (AFD_WPT_MIRROR_COPY): after the barrier that ends a stored level all threads copy
+// pos[n-1+i] = pos[n-1-i] (lanes walk along the padding of a node: conflict free) and a second barrier follows; the
+// right-edge items then carry no mirror stores at all.
+#ifndef AFD_WPT_MIRROR_COPY
+#define AFD_WPT_MIRROR_COPY 0
+#endif
 #ifndef AFD_WPT_KO_MIRRORS
 #define AFD_WPT_KO_MIRRORS 0      // knock-out timing: 1 skips the mirror (padding) stores of the edge items -- wrong results
 #endif
@@ -431,7 +437,7 @@ __device__ __forceinline__ void edge_store(float* __restrict__ node, const float
             pos[k] = v[r];
             if (!REFL && !AFD_WPT_KO_MIRRORS && k >= 1 && k <= padl) pos[-k] = v[r];
             const int mr = n_out - 1 - k;
-            if (!(REFL && AFD_WPT_REFLECT_RIGHT) && !AFD_WPT_KO_MIRRORS && mr >= 1 && mr <= padr) pos[n_out - 1 + mr] = v[r];
+            if (!(REFL && AFD_WPT_REFLECT_RIGHT) && !AFD_WPT_MIRROR_COPY && !AFD_WPT_KO_MIRRORS && mr >= 1 && mr <= padr) pos[n_out - 1 + mr] = v[r];
         }
     }
 }
@@ -474,13 +480,29 @@ __device__ __forceinline__ void right_store(float* __restrict__ plo, float* __re
     }
 #pragma unroll
     for (int r = 0; r < R; ++r)
-        if (!(REFL && AFD_WPT_REFLECT_RIGHT) && !AFD_WPT_KO_MIRRORS && static_cast<unsigned>(q - r - 1) < static_cast<unsigned>(padr)) { mlo[-r] = lo[r]; mhi[-r] = hi[r]; }
+        if (!(REFL && AFD_WPT_REFLECT_RIGHT) && !AFD_WPT_MIRROR_COPY && !AFD_WPT_KO_MIRRORS && static_cast<unsigned>(q - r - 1) < static_cast<unsigned>(padr)) { mlo[-r] = lo[r]; mhi[-r] = hi[r]; }
 }
 
 template <int R>
 __device__ __forceinline__ void scale_all(float (&lo)[R], float (&hi)[R], float mul) {
 #pragma unroll
     for (int r = 0; r < R; ++r) { lo[r] *= mul; hi[r] *= mul; }
+}
+
+// Right reflect padding of `nodes` stored nodes of length n: pos[n-1+i] = pos[n-1-i], i = 1 .. F-2 (+1 if n is odd).
+template <int F>
+__device__ __forceinline__ void mirror_copy(float* __restrict__ base, int nodes, int n, int stride) {
+    constexpr int padl = F - 2;
+    if constexpr (padl == 0) return;
+    const bool odd = (n & 1) != 0;
+    const int padr = padl + (odd ? 1 : 0);
+    const int total = nodes * padr;
+    for (int idx = threadIdx.x; idx < total; idx += kThreads) {
+        const int node = odd ? idx / (padl + 1) : idx / (padl > 0 ? padl : 1);
+        const int mr = idx - node * padr + 1;
+        float* pos = base + node * stride + padl + (n - 1);
+        pos[mr] = pos[-mr];
+    }
 }
 
 // One stored tree level: `parents` padded nodes in `in` -> 2*parents padded nodes in `out`.
@@ -755,6 +777,12 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
             level1_chunk<F, R1, REFL>((j & 1) ? buf1 : buf0, regA, kb, ke, n1, sp1, t1, t1p);
         }
         __syncthreads();
+        if constexpr (AFD_WPT_MIRROR_COPY != 0) {
+            if (L > 1) {
+                mirror_copy<F>(regA, 1, n1, plan.stride1);
+                __syncthreads();
+            }
+        }
         float* out_b = out + b * C * static_cast<long long>(T) * P;
         if (L == 1) {
             // the level-1 node is the output: epilogue straight from shared memory (rare configuration)
@@ -788,6 +816,10 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
                 if (ps.rsel == 0) mid_level<F, RA, LAT, REFL>(smem + ps.in_off, smem + ps.out_off, ps, cf);
                 else mid_level<F, RB, LAT, REFL>(smem + ps.in_off, smem + ps.out_off, ps, cf);
                 __syncthreads();
+                if constexpr (AFD_WPT_MIRROR_COPY != 0) {
+                    mirror_copy<F>(smem + ps.out_off, 2 * ps.parents, ps.n_out, ps.out_stride);
+                    __syncthreads();
+                }
             } else {
                 if (ps.prefetch && nb < 2 * B) {
                     issue_chunk<F>(x + (nb >> 1) * x_row_stride, buf0, 0, plan);
