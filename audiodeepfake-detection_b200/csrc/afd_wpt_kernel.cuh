@@ -249,9 +249,16 @@ struct ReflOk {
 // Right padding by a copy pass (AFD_WPT_MIRROR_COPY): after the barrier that ends a stored level all threads copy
 // pos[n-1+i] = pos[n-1-i] (lanes walk along the padding of a node: conflict free) and a second barrier follows; the
 // right-edge items then carry no mirror stores at all.
+// Measured (same-box A/B, bit-identical): coif4 (F = 24) -2.3 % time, sym5 (F = 10) +0.3 %: the two extra barriers per level
+// pay only when the padding is long, so the copy pass is used for F >= kMirrorCopyMinF.
 #ifndef AFD_WPT_MIRROR_COPY
-#define AFD_WPT_MIRROR_COPY 0
+#define AFD_WPT_MIRROR_COPY 1
 #endif
+constexpr int kMirrorCopyMinF = 16;
+template <int F>
+struct MirrorCopy {
+    static constexpr bool value = AFD_WPT_MIRROR_COPY != 0 && F >= kMirrorCopyMinF;
+};
 #ifndef AFD_WPT_KO_MIRRORS
 #define AFD_WPT_KO_MIRRORS 0      // knock-out timing: 1 skips the mirror (padding) stores of the edge items -- wrong results
 #endif
@@ -426,7 +433,7 @@ __device__ __forceinline__ void vec_store(float* __restrict__ dst, const float (
 
 // Generic guarded store of R coefficients of a child node plus their mirror images into the node's padding.
 // `node` points at the first padding sample; coefficient k lives at node[padl + k].
-template <int R, bool REFL>
+template <int R, bool REFL, bool MC>
 __device__ __forceinline__ void edge_store(float* __restrict__ node, const float (&v)[R], int k0, int n_out, int padl) {
     const int padr = padl + (n_out & 1);
     float* pos = node + padl;
@@ -437,7 +444,7 @@ __device__ __forceinline__ void edge_store(float* __restrict__ node, const float
             pos[k] = v[r];
             if (!REFL && !AFD_WPT_KO_MIRRORS && k >= 1 && k <= padl) pos[-k] = v[r];
             const int mr = n_out - 1 - k;
-            if (!(REFL && AFD_WPT_REFLECT_RIGHT) && !AFD_WPT_MIRROR_COPY && !AFD_WPT_KO_MIRRORS && mr >= 1 && mr <= padr) pos[n_out - 1 + mr] = v[r];
+            if (!(REFL && AFD_WPT_REFLECT_RIGHT) && !MC && !AFD_WPT_KO_MIRRORS && mr >= 1 && mr <= padr) pos[n_out - 1 + mr] = v[r];
         }
     }
 }
@@ -461,7 +468,7 @@ __device__ __forceinline__ void left_store(float* __restrict__ plo, float* __res
 // Right-edge chunk of a pair of sibling nodes (no left-mirrored coefficient inside): outputs k0+r are valid for
 // r <= q = n_out-1-k0 and mirrored to n_out-1+mr (mr = q - r) for 1 <= mr <= padr; one predicate pair serves both
 // channels.  plo / phi point at coefficient 0.
-template <int R, bool REFL>
+template <int R, bool REFL, bool MC>
 __device__ __forceinline__ void right_store(float* __restrict__ plo, float* __restrict__ phi, const float (&lo)[R],
                                             const float (&hi)[R], int k0, int n_out, int padl) {
     const int padr = padl + (n_out & 1);
@@ -480,7 +487,7 @@ __device__ __forceinline__ void right_store(float* __restrict__ plo, float* __re
     }
 #pragma unroll
     for (int r = 0; r < R; ++r)
-        if (!(REFL && AFD_WPT_REFLECT_RIGHT) && !AFD_WPT_MIRROR_COPY && !AFD_WPT_KO_MIRRORS && static_cast<unsigned>(q - r - 1) < static_cast<unsigned>(padr)) { mlo[-r] = lo[r]; mhi[-r] = hi[r]; }
+        if (!(REFL && AFD_WPT_REFLECT_RIGHT) && !MC && !AFD_WPT_KO_MIRRORS && static_cast<unsigned>(q - r - 1) < static_cast<unsigned>(padr)) { mlo[-r] = lo[r]; mhi[-r] = hi[r]; }
 }
 
 template <int R>
@@ -543,10 +550,10 @@ __device__ __forceinline__ void mid_level(const float* __restrict__ in, float* _
             const bool left = c < sp.CL, right = c >= sp.CR;
             if (left && !right && c == 0) left_store<R, padl, 0, REFL>(d0 + padl, d1 + padl, lo, hi);
             else if (left && !right && c == 1) left_store<R, padl, 1, REFL>(d0 + padl, d1 + padl, lo, hi);
-            else if (right && !left) right_store<R, REFL>(d0 + padl, d1 + padl, lo, hi, k0, n_out, padl);
+            else if (right && !left) right_store<R, REFL, MirrorCopy<F>::value>(d0 + padl, d1 + padl, lo, hi, k0, n_out, padl);
             else {
-                edge_store<R, REFL>(d0, lo, k0, n_out, padl);
-                edge_store<R, REFL>(d1, hi, k0, n_out, padl);
+                edge_store<R, REFL, MirrorCopy<F>::value>(d0, lo, k0, n_out, padl);
+                edge_store<R, REFL, MirrorCopy<F>::value>(d1, hi, k0, n_out, padl);
             }
         }
     }
@@ -570,7 +577,7 @@ __device__ __forceinline__ void level1_chunk(const float* __restrict__ buf, floa
         if constexpr (AFD_WPT_FFMA2 != 0 && F <= AFD_WPT_PACKED_FIR_MAXF) fir1_packed<F, R>(w, t2, y);
         else fir1<F, R>(w, t, y);
         if (c >= sp.CL && c < sp.CIe) vec_store<R>(node + padl + k0, y);
-        else edge_store<R, REFL>(node, y, k0, n_out, padl);
+        else edge_store<R, REFL, MirrorCopy<F>::value>(node, y, k0, n_out, padl);
     }
 }
 // Chunks are cut at multiples of R, so only the last chunk (ke == n_out) holds a partial item.
@@ -777,7 +784,7 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
             level1_chunk<F, R1, REFL>((j & 1) ? buf1 : buf0, regA, kb, ke, n1, sp1, t1, t1p);
         }
         __syncthreads();
-        if constexpr (AFD_WPT_MIRROR_COPY != 0) {
+        if constexpr (MirrorCopy<F>::value) {
             if (L > 1) {
                 mirror_copy<F>(regA, 1, n1, plan.stride1);
                 __syncthreads();
@@ -816,7 +823,7 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
                 if (ps.rsel == 0) mid_level<F, RA, LAT, REFL>(smem + ps.in_off, smem + ps.out_off, ps, cf);
                 else mid_level<F, RB, LAT, REFL>(smem + ps.in_off, smem + ps.out_off, ps, cf);
                 __syncthreads();
-                if constexpr (AFD_WPT_MIRROR_COPY != 0) {
+                if constexpr (MirrorCopy<F>::value) {
                     mirror_copy<F>(smem + ps.out_off, 2 * ps.parents, ps.n_out, ps.out_stride);
                     __syncthreads();
                 }
