@@ -17,9 +17,11 @@
 //     stores of the levels where the pending factor leaves [1e-9, 1e9] and into the epilogue of the last level.
 //     Filters whose lattice is not trustworthy (residual, reflection, F > 32) use the direct form.
 //   * Intermediate levels live in two ping-pong shared-memory regions (odd levels in A, even levels and the
-//     frame staging buffers in B).  Every node is stored WITH its reflect padding materialised (F-2 mirrored
-//     samples left, F-2 (+1) right), written by the threads that produce the mirrored coefficients.  Every
-//     work item of the next level is therefore a plain aligned window: no index reflection on the read side.
+//     frame staging buffers in B).  Every node is stored with room for its reflect padding (F-2 samples left,
+//     F-2 (+1) right), so every work item of the next level is a plain aligned window.  The right padding is
+//     materialised (by the threads that produce the mirrored coefficients, or by a copy pass for F >= 16); the
+//     left padding is not written: its only reader, chunk 0 of the next level, mirrors its own register window
+//     (see ReflOk below; nodes with an item size R < F/2 keep the left mirror stores).
 //   * Work item = R consecutive output pairs of one node: 128-bit LDS of the 2R+F-2 window (conflict-free for
 //     R/2 odd), the FIR / lattice on registers with tap operands from the constant bank, 64-bit STS.  R is picked
 //     per level (two instantiations) so that the item count fills whole rounds of the 256 threads.
