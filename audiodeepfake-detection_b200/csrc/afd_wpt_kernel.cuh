@@ -261,6 +261,10 @@ template <int F>
 struct MirrorCopy {
     static constexpr bool value = AFD_WPT_MIRROR_COPY != 0 && F >= kMirrorCopyMinF;
 };
+// With the left padding gone the first chunks of a node are ordinary interior items (lanes along the node, vector stores).
+#ifndef AFD_WPT_REFL_INTERIOR
+#define AFD_WPT_REFL_INTERIOR 1
+#endif
 #ifndef AFD_WPT_KO_MIRRORS
 #define AFD_WPT_KO_MIRRORS 0      // knock-out timing: 1 skips the mirror (padding) stores of the edge items -- wrong results
 #endif
@@ -409,11 +413,11 @@ struct Split {
 };
 __host__ __device__ inline unsigned magic_of(int d) { return d > 0 ? static_cast<unsigned>(0xFFFFFFFFu / static_cast<unsigned>(d)) + 1u : 0u; }
 
-__host__ __device__ inline Split make_split(int n_out, int R, int padl) {
+__host__ __device__ inline Split make_split(int n_out, int R, int padl, bool no_left = false) {
     Split s;
     s.C = (n_out + R - 1) / R;
     const int padr = padl + (n_out & 1);
-    int cl = padl == 0 ? 0 : padl / R + 1;
+    int cl = (padl == 0 || no_left) ? 0 : padl / R + 1;    // no_left: the left padding is not stored (ReflOk): no left-edge chunks
     int cie = (n_out - 1 - padr) / R;            // chunks c < cie end before the first right-mirrored coefficient
     if (n_out - 1 - padr < 0) cie = 0;
     s.CR = cie;
@@ -750,7 +754,7 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
     const int C = (ep.log_scale && ep.sign_channel) ? 2 : 1;
     const int T = plan.T;
     const int n1 = plan.n1;
-    const Split sp1 = make_split(n1, R1, padl);
+    const Split sp1 = make_split(n1, R1, padl, REFL && AFD_WPT_REFL_INTERIOR);
     const int half_base = L >= 2 ? half << (L - 2) : 0;   // natural index of the half tree's first level-(L-1) node
     // the CTA's level-1 filter
     float t1[F];
@@ -881,6 +885,9 @@ static int make_plan(int64_t N, int F, int L, const Tuning& tu, int ctas_per_sm,
     p->n1 = n[1];
     p->T = n[L];
     const int padl = F - 2;
+    int minR = tu.RA;
+    for (int r : {tu.RB, tu.RLA, tu.RLB}) minR = r < minR ? r : minR;
+    const bool refl_ok = AFD_WPT_REFLECT_REGS != 0 && minR >= F / 2;      // == ReflOk<F, RA, RB, RLA, RLB> of the launched kernel
     const int limit_floats = ((ctas_per_sm == 2 ? (228 * 1024 / 2 - 1024) : kMaxSmemPerCta) - shave_bytes) / 4;
     int maxR = tu.R1;
     for (int r : {tu.RA, tu.RB, tu.RLA, tu.RLB}) maxR = r > maxR ? r : maxR;
@@ -924,7 +931,7 @@ static int make_plan(int64_t N, int F, int L, const Tuning& tu, int ctas_per_sm,
         return level_cost(nodes, n_out, rb, tu.halo) < level_cost(nodes, n_out, ra, tu.halo) ? 1 : 0;
     };
     auto fill_split = [&](Pass& ps, int R) {
-        const Split sp = make_split(ps.n_out, R, padl);
+        const Split sp = make_split(ps.n_out, R, padl, refl_ok && AFD_WPT_REFL_INTERIOR);
         ps.C = sp.C; ps.CL = sp.CL; ps.CIe = sp.CIe; ps.CR = sp.CR; ps.NI = sp.NI; ps.NE = sp.NE; ps.magicNI = sp.magicNI;
     };
     auto stored_mul = [&]() {                                 // factor for a stored level
