@@ -256,7 +256,10 @@ struct ReflOk {
 #ifndef AFD_WPT_MIRROR_COPY
 #define AFD_WPT_MIRROR_COPY 1
 #endif
-constexpr int kMirrorCopyMinF = 16;
+#ifndef AFD_WPT_MIRROR_COPY_MINF
+#define AFD_WPT_MIRROR_COPY_MINF 16
+#endif
+constexpr int kMirrorCopyMinF = AFD_WPT_MIRROR_COPY_MINF;
 template <int F>
 struct MirrorCopy {
     static constexpr bool value = AFD_WPT_MIRROR_COPY != 0 && F >= kMirrorCopyMinF;
