@@ -93,7 +93,7 @@ def strip_ddp_prefix(state: dict) -> dict:
 
 def load_reference_checkpoint(path: str, time_len: int, time_dim_add: int, map_location="cpu") -> DCNN:
     """Load one of reference models/*.pt ({'MODEL_STATE', 'EPOCHS_RUN'}) into a matching DCNN (eval mode)."""
-    snap = torch.load(path, map_location=map_location, weights_only=False)
+    snap = torch.load(path, map_location=map_location, weights_only=True)
     state = strip_ddp_prefix(snap["MODEL_STATE"] if "MODEL_STATE" in snap else snap)
     stem = "pooled" if "cnn.18.weight" in state else "strided"
     model = DCNN(DCNNConfig(time_len=time_len, time_dim_add=time_dim_add, stem=stem))

@@ -15,9 +15,13 @@ Inputs must be CUDA fp32 tensors; there is no CPU fallback.
 from __future__ import annotations
 
 import ctypes
+import io
+import os
+import pickle
 from math import log
 from typing import Optional
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -59,6 +63,8 @@ def _norm_array(norm, channels: int):
     """(mean, std) scalars / per-channel sequences -> ctypes float[C][2] for the fused Normalize epilogue."""
     if norm is None:
         return None
+    if isinstance(norm, HostNorm):                  # converted once by fuse_normalize: no device sync per step
+        return norm.array(channels)
     mean, std = norm
     mean = torch.as_tensor(mean, dtype=torch.float32).reshape(-1).tolist()
     std = torch.as_tensor(std, dtype=torch.float32).reshape(-1).tolist()
@@ -72,6 +78,24 @@ def _norm_array(norm, channels: int):
     for m, sd in zip(mean, std):
         flat += [m, sd]
     return (ctypes.c_float * (2 * channels))(*flat)
+
+
+class HostNorm:
+    """(mean, std) of the fused Normalize epilogue as host floats, read from the device ONCE (``fuse_normalize``);
+    ``get_transforms`` / ``calc_normalization`` hand out CUDA tensors, and converting them on every forward would
+    be a blocking device-to-host copy per training step."""
+
+    def __init__(self, mean, std):
+        self.mean = torch.as_tensor(mean, dtype=torch.float32).reshape(-1).tolist()
+        self.std = torch.as_tensor(std, dtype=torch.float32).reshape(-1).tolist()
+        self._arrays = {}
+
+    def array(self, channels: int):
+        arr = self._arrays.get(channels)
+        if arr is None:
+            arr = _norm_array((self.mean, self.std), channels)
+            self._arrays[channels] = arr
+        return arr
 
 
 def wavelet_packet_features(pt_data: torch.Tensor, wavelet, max_lev: int = 8, log_scale: bool = False,
@@ -370,23 +394,80 @@ def _opt(args, name: str, default):
     """Optional flag of the reference's DotDict (utils.py:321-395: attribute access is dict lookup, so a missing
     key may raise KeyError instead of AttributeError)."""
     try:
-        return getattr(args, name)
+        value = getattr(args, name)
     except (AttributeError, KeyError):
         return default
+    return default if value is None else value
+
+
+class _ArrayUnpickler(pickle.Unpickler):
+    """The reference caches ``[mean, std]`` as a pickled list of numpy arrays (wavelet_math.py:449-450); nothing but
+    numpy array reconstruction is allowed to run while reading such a file back."""
+
+    _ALLOWED = {("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+                ("numpy", "ndarray"), ("numpy", "dtype"), ("numpy.core.multiarray", "scalar"),
+                ("numpy._core.multiarray", "scalar")}
+
+    def find_class(self, module, name):
+        if (module, name) in self._ALLOWED:
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f"unexpected object {module}.{name} in a mean/std cache file")
+
+
+def norm_cache_prefix(args) -> Optional[str]:
+    """``norm_dir`` of the reference (wavelet_math.py:327-347): the cache file is ``f"{prefix}_mean_std.pkl"``.
+    ``None`` when ``args`` does not carry the flags the name is built from (e.g. a bare benchmark config)."""
+    try:
+        loss_less = "_loss_less" if args.loss_less == "True" else ""
+        return (args.log_dir + "/norms/" + args.data_path.replace("/", "_") + "_" + "-".join(args.only_use) + "_"
+                + args.transform + "_" + args.wavelet + "_" + str(args.num_of_scales) + "_" + str(args.power)
+                + loss_less + "_" + str(args.sample_rate) + "_" + str(args.seconds) + "secs")
+    except (AttributeError, KeyError, TypeError):
+        return None
+
+
+def _training_batches(args):
+    """The batches the reference's ``calc_normalization`` iterates (wavelet_math.py:406-431).  Dataset and wav I/O are
+    the reference's own (out of scope here): an iterable / DataLoader in ``args.norm_batches`` is used as is,
+    otherwise the reference's ``get_costum_dataset`` is imported when this module runs inside the reference tree."""
+    batches = _opt(args, "norm_batches", None)
+    if batches is not None:
+        return batches
+    get_costum_dataset = None
+    for mod in ("audiofakedetect.data_loader", "src.audiofakedetect.data_loader"):
+        try:
+            get_costum_dataset = __import__(mod, fromlist=["get_costum_dataset"]).get_costum_dataset
+            break
+        except Exception:      # noqa: BLE001  (the reference package needs ptwt / pywt / librosa at import time)
+            continue
+    if get_costum_dataset is None:
+        raise RuntimeError(
+            "get_transforms(normalization=True): no cached '<norm_dir>_mean_std.pkl', no args.norm_batches, and the "
+            "reference's audiofakedetect.data_loader (which builds the training set) is not importable here")
+    asv = _opt(args, "asvspoof_name", None)
+    dataset = get_costum_dataset(
+        data_path=args.data_path, ds_type="train", only_use=args.only_use, save_path=args.save_path,
+        limit=args.limit_train[0], asvspoof_name=(f"{asv}_T" if asv is not None and "LA" in asv else asv),
+        file_type=args.file_type, resample_rate=args.sample_rate, seconds=args.seconds)
+    return torch.utils.data.DataLoader(dataset, batch_size=4000, shuffle=False, pin_memory=True,
+                                       num_workers=_opt(args, "num_workers", 0))
 
 
 def get_transforms(args, features: str, device: str, normalization: bool, pbar: bool = False,
                    verbose: bool = True, norm_batches=None) -> tuple[torch.nn.Sequential, torch.nn.Sequential]:
-    """Initialize transformations and normalize (reference wavelet_math.py:266-384).
+    """Initialize transformations and normalize (reference wavelet_math.py:266-384, same positional signature).
 
     ``args`` needs the reference's flag names: transform, num_of_scales, hop_length, log_scale, power, wavelet,
-    loss_less ("True"/"False" strings), features, block_norm, mean, std.  With ``normalization=True`` the
-    statistics are computed by ``calc_normalization`` over ``norm_batches`` -- an iterable of audio batches
-    standing in for the reference's training-set DataLoader (:396-424; dataset and wav I/O are out of scope
-    here); otherwise ``args.mean`` / ``args.std`` are used (:368-371).
+    loss_less ("True"/"False" strings), features, block_norm, mean, std.  Normalisation statistics, in the
+    reference's order (:349-371): (1) a cached ``<norm_dir>_mean_std.pkl`` (the reference's own file format and
+    name) is loaded when it exists; (2) with ``normalization=True`` they are computed by ``calc_normalization`` --
+    statistics-only launches over ``norm_batches`` / ``args.norm_batches`` or, inside the reference tree, over the
+    reference's training DataLoader -- and cached under the same name; (3) otherwise ``args.mean`` / ``args.std``.
     """
     if features not in ("none", None):
-        raise NotImplementedError("only features='none' is on the accelerated path (lfcc/delta are out of scope)")
+        raise NotImplementedError(
+            f"features={features!r}: the reference appends LFCC / ComputeDeltas modules here (wavelet_math.py:316-323); "
+            "they are outside the accelerated hot path (SURVEY.md section 2.1 row 5) -- use features='none'")
     if args.transform == "stft":
         transform = STFTLayer(
             n_fft=args.num_of_scales * 2 - 1,
@@ -403,20 +484,35 @@ def get_transforms(args, features: str, device: str, normalization: bool, pbar: 
             power=args.power,
             block_norm_dict=None,
             block_norm=False,
-            # the reference hard-codes True (:304) and the trainer discards the result (train_classifier.py:966);
-            # here the statistics are fused into the kernel and opt-in, to keep tiny batches launch-lean
-            compute_welford=bool(_opt(args, "compute_welford", False)),
+            # the reference hard-codes True (:304): aux is the dict of 2^level per-node estimators.  Here the
+            # statistics are a side reduction of the one launch; args.compute_welford=False opts out.
+            compute_welford=bool(_opt(args, "compute_welford", True)),
         )
     else:
         raise ValueError(f"unknown transform '{args.transform}'")
     transforms = torch.nn.Sequential(transform)
     block_norm = bool(_opt(args, "block_norm", False))
     welford_dict = None
-    if normalization:
-        if norm_batches is None:
-            raise ValueError("normalization=True needs norm_batches (audio batches of the training set)")
-        welford_dict, mean, std = calc_normalization(transforms, norm_batches)
+    prefix = norm_cache_prefix(args)
+    if prefix is not None and not block_norm and os.path.exists(f"{prefix}_mean_std.pkl"):      # reference :349-355
+        if verbose:
+            print("Loading pre calculated mean and std from file.")
+        with open(f"{prefix}_mean_std.pkl", "rb") as file:
+            mean, std = _ArrayUnpickler(io.BytesIO(file.read())).load()
+        mean = torch.from_numpy(np.asarray(mean).astype(np.float32)).to(device)
+        std = torch.from_numpy(np.asarray(std).astype(np.float32)).to(device)
+    elif normalization:                                                                          # reference :364-367
+        if verbose:
+            print("computing mean and std values.", flush=True)
+        batches = norm_batches if norm_batches is not None else _training_batches(args)
+        welford_dict, mean, std = calc_normalization(transforms, batches)
+        if prefix is not None and not block_norm:                                                # reference :449-450
+            os.makedirs(os.path.dirname(prefix), exist_ok=True)
+            with open(f"{prefix}_mean_std.pkl", "wb") as file:
+                pickle.dump([mean.cpu().numpy(), std.cpu().numpy()], file)
     else:
+        if verbose:
+            print("Using default mean and std.")
         mean = torch.as_tensor(args.mean, dtype=torch.float32, device=device)
         std = torch.as_tensor(args.std, dtype=torch.float32, device=device)
     if block_norm:                                        # reference :373-378
@@ -473,7 +569,7 @@ def fuse_normalize(transforms: torch.nn.Sequential, normalize: torch.nn.Sequenti
     epilogue: returns ``(transforms, identity)`` so callers keep the two-step call pattern
     (train_classifier.py:965-967) while the features touch HBM once."""
     norm = normalize[0]
-    transforms[0].fused_norm = (norm.mean, norm.std)
+    transforms[0].fused_norm = HostNorm(norm.mean, norm.std)
     return transforms, torch.nn.Sequential(torch.nn.Identity())
 
 

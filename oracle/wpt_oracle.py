@@ -40,8 +40,27 @@ def level_lengths(n, F, level):
     return out
 
 
-def dwt_step(x, dec_lo, dtype=np.float32):
-    """One analysis step on the last axis: returns (lo, hi).  ptwt wavedec(level=1, mode='reflect')."""
+def extension_index(idx, n, mode):
+    """Signal-extension index maps as PyWavelets documents them (pywt "Signal extension modes"; pywt.pad is
+    numpy.pad for these): 'reflect' = whole-sample symmetric ... x2 x1 | x0 x1 .. xn-1 | xn-2 xn-3 ...;
+    'symmetric' = half-sample symmetric ... x1 x0 | x0 x1 .. xn-1 | xn-1 xn-2 ... (pywt's default mode, used by
+    the published examples); 'zero' returns -1 for positions outside the signal."""
+    if mode == "reflect":
+        return reflect_index(idx, n)
+    if mode == "symmetric":
+        period = 2 * n
+        idx = np.mod(idx, period)
+        return np.where(idx >= n, period - 1 - idx, idx)
+    if mode == "zero":
+        return np.where((idx < 0) | (idx >= n), -1, idx)
+    raise ValueError(mode)
+
+
+def dwt_step(x, dec_lo, dtype=np.float32, mode="reflect"):
+    """One analysis step on the last axis: returns (lo, hi).  ptwt wavedec(level=1, mode='reflect').
+
+    ``mode`` other than 'reflect' exists only so that the published PyWavelets examples (which use pywt's default
+    'symmetric' mode, or 'zero' in ptwt's README) can pin the convolution phase and tap orientation."""
     x = np.asarray(x, dtype=dtype)
     h = np.asarray(dec_lo, dtype=np.float64)
     g = _dec_hi(h)
@@ -49,8 +68,11 @@ def dwt_step(x, dec_lo, dtype=np.float32):
     n = x.shape[-1]
     padl = F - 2
     padr = F - 2 + (n % 2)
-    idx = reflect_index(np.arange(-padl, n + padr), n)
-    xp = x[..., idx]
+    idx = extension_index(np.arange(-padl, n + padr), n, mode)
+    if mode == "zero":
+        xp = np.where(idx >= 0, x[..., np.maximum(idx, 0)], dtype(0))
+    else:
+        xp = x[..., idx]
     win = np.lib.stride_tricks.sliding_window_view(xp, F, axis=-1)[..., ::2, :]
     # conv1d is a correlation, ptwt flips the filters: taps applied are h[::-1]
     lo = win @ h[::-1].astype(dtype)
@@ -74,14 +96,14 @@ def natural_paths(level):
     return order
 
 
-def wavelet_packet_tree(x, dec_lo, level, dtype=np.float32):
+def wavelet_packet_tree(x, dec_lo, level, dtype=np.float32, mode="reflect"):
     """All nodes down to ``level``: dict path -> array[..., L_level]."""
     tree = {"": np.asarray(x, dtype=dtype)}
     frontier = [""]
     for _ in range(level):
         nxt = []
         for p in frontier:
-            lo, hi = dwt_step(tree[p], dec_lo, dtype)
+            lo, hi = dwt_step(tree[p], dec_lo, dtype, mode)
             tree[p + "a"], tree[p + "d"] = lo, hi
             nxt += [p + "a", p + "d"]
         frontier = nxt

@@ -27,7 +27,11 @@ def _run(x, name, level, **kw):
 
 
 @pytest.mark.parametrize("name,level,B", [("sym5", 8, 5), ("coif4", 8, 4), ("db8", 7, 3), ("haar", 8, 3),
-                                          ("db2", 8, 2), ("sym8", 7, 2), ("db10", 8, 2), ("coif2", 6, 2)])
+                                          ("db2", 8, 2), ("sym8", 7, 2), ("db10", 8, 2), ("coif2", 6, 2),
+                                          # coif5 .. coif10 of scripts/start_exps.sh:26-31 (F = 30 .. 60; 54 and 60 taps
+                                          # run one CTA per SM)
+                                          ("coif5", 8, 2), ("coif6", 8, 2), ("coif7", 8, 2), ("coif8", 8, 2),
+                                          ("coif9", 8, 2), ("coif10", 8, 3)])
 def test_raw_coefficients_match_oracle(name, level, B):
     rng = np.random.default_rng(1)
     x = (rng.standard_normal((B, 22050)) * 0.1).astype(np.float32)
