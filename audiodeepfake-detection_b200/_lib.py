@@ -18,6 +18,7 @@ AFD_ORDER_NATURAL = 1
 SIGNATURES = {
     "afd_version": (c_int, []),
     "afd_last_error": (c_char_p, []),
+    "afd_source_hash": (c_char_p, []),
     "afd_wpt_out_len": (c_int, [c_int64, c_int, c_int, POINTER(c_int64)]),
     "afd_wpt_forward": (c_int, [c_void_p, c_int64, c_int64, c_int64, POINTER(c_double), c_int, c_int, c_int,
                                 c_float, c_int, c_float, c_int, c_void_p, POINTER(c_int64), c_void_p]),

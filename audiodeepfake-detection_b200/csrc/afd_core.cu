@@ -46,7 +46,15 @@ __global__ void __launch_bounds__(256, 4) fma_probe_kernel(float* sink, float a,
 
 using namespace afd;
 
-extern "C" int afd_version(void) { return 100; }
+extern "C" int afd_version(void) { return 200; }
+
+// Build provenance: sha256 of csrc/* + include/afd_b200.h as computed by build.py (source_hash()) when this unit was
+// compiled; build.py reads the marker back from the file to decide whether the binary matches the sources on disk.
+#ifndef AFD_SOURCE_HASH
+#define AFD_SOURCE_HASH "unknown"
+#endif
+static const char kSourceHash[] = "AFD_SOURCE_HASH=" AFD_SOURCE_HASH;
+extern "C" const char* afd_source_hash(void) { return kSourceHash + 16; }
 
 extern "C" const char* afd_last_error(void) { return g_err; }
 
@@ -57,23 +65,28 @@ extern "C" int afd_measure_fp32_fma_tflops(int iters, double* tflops, void* stre
     AFD_CUDA_TRY(cudaGetDevice(&dev));
     AFD_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     float* sink = nullptr;
-    AFD_CUDA_TRY(cudaMalloc(&sink, 4));
-    cudaEvent_t e0, e1;
-    AFD_CUDA_TRY(cudaEventCreate(&e0));
-    AFD_CUDA_TRY(cudaEventCreate(&e1));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     const int inner = 4096;
     const int grid = sms * 8;
-    fma_probe_kernel<<<grid, 256, 0, s>>>(sink, 0.999f, 0.001f, inner);  // warm-up
-    AFD_CUDA_TRY(cudaEventRecord(e0, s));
-    for (int i = 0; i < iters; ++i) fma_probe_kernel<<<grid, 256, 0, s>>>(sink, 0.999f, 0.001f, inner);
-    AFD_CUDA_TRY(cudaEventRecord(e1, s));
-    AFD_CUDA_TRY(cudaEventSynchronize(e1));
     float ms = 0.f;
-    AFD_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaError_t e = cudaMalloc(&sink, 4);
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e == cudaSuccess) {
+        fma_probe_kernel<<<grid, 256, 0, s>>>(sink, 0.999f, 0.001f, inner);  // warm-up
+        e = cudaEventRecord(e0, s);
+    }
+    if (e == cudaSuccess) {
+        for (int i = 0; i < iters; ++i) fma_probe_kernel<<<grid, 256, 0, s>>>(sink, 0.999f, 0.001f, inner);
+        e = cudaEventRecord(e1, s);
+    }
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    if (e0) cudaEventDestroy(e0);          // released on every path
+    if (e1) cudaEventDestroy(e1);
+    if (sink) cudaFree(sink);
+    if (e != cudaSuccess) return cuda_fail(e, "afd_measure_fp32_fma_tflops");
     const double flops = 2.0 * 8 * 16 * double(inner) * 256.0 * grid * iters;
     *tflops = flops / (ms * 1e-3) / 1e12;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(sink);
     return AFD_OK;
 }

@@ -160,8 +160,8 @@ extern "C" int afd_haar_fingerprint_host(const float* x_host, int64_t B, int64_t
                                                                           reinterpret_cast<int64_t*>(d_count), s);
                                     });
     if (rc == AFD_OK) {
-        AFD_CUDA_TRY(cudaSetDevice(device));
-        e = cudaMemcpy(sums_host, d_sums, P * sizeof(double), cudaMemcpyDeviceToHost);
+        e = cudaSetDevice(device);
+        if (e == cudaSuccess) e = cudaMemcpy(sums_host, d_sums, P * sizeof(double), cudaMemcpyDeviceToHost);
         long long cnt = 0;
         if (e == cudaSuccess) e = cudaMemcpy(&cnt, d_count, sizeof(long long), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = cuda_fail(e, "D2H copy of sums");

@@ -632,7 +632,7 @@ __device__ __forceinline__ void last_level(const float* __restrict__ in, const P
         const int nv = T - k0;                                         // rows r < nv exist
         if constexpr (extended) {
             if (ep.node_stats) {                                       // statistics of the raw coefficients
-                if (ts.col[0] != col_lo) {                             // never taken when stats_simple
+                if (ts.col[0] != col_lo) {                             // taken once per launch when stats_simple
                     flush_node_stats(ep, P, ts);
                     ts.col[0] = col_lo; ts.col[1] = col_hi;
                 }
@@ -1022,13 +1022,6 @@ static int launch(const float* x, int64_t B, int64_t N, int64_t x_row_stride, fl
         }
         return AFD_OK;
     }
-    Epilogue epk = ep;
-    {
-        int last_passes = 0, parents = 0;
-        for (int i = 0; i < plan.npass; ++i)
-            if (plan.pass[i].kind == 1) { ++last_passes; parents = plan.pass[i].parents; }
-        epk.stats_simple = (last_passes == 1 && parents <= kThreads && kThreads % parents == 0) ? 1 : 0;
-    }
     Coefs<F> cf;
     for (int k = 0; k < F; ++k) {
         cf.lo[k] = static_cast<float>(dec_lo[k]);
@@ -1055,6 +1048,13 @@ static int launch(const float* x, int64_t B, int64_t N, int64_t x_row_stride, fl
             rc = make_plan(N, F, L, tu, 1, lat.scale, &plan);
             if (rc != AFD_OK) return rc;
         }
+    }
+    Epilogue epk = ep;
+    {   // derived from the plan that is actually launched (the occupancy fallback above may have re-planned)
+        int last_passes = 0, parents = 0;
+        for (int i = 0; i < plan.npass; ++i)
+            if (plan.pass[i].kind == 1) { ++last_passes; parents = plan.pass[i].parents; }
+        epk.stats_simple = (last_passes == 1 && parents <= kThreads && kThreads % parents == 0) ? 1 : 0;
     }
     const int smem = 4 * plan.smem_floats;
     long long grid = 2LL * sms * ctas / 2 * 2;             // persistent: every resident slot, even count

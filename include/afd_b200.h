@@ -40,6 +40,10 @@ int afd_version(void);
 
 /* Thread-local message for the most recent failing call on this thread ("" if none). */
 const char* afd_last_error(void);
+/* Build provenance: sha256 (hex) of csrc/ + include/afd_b200.h the library was compiled from -- equals
+ * audiodeepfake-detection_b200/build.py:source_hash() when the binary matches the sources on disk; "unknown" for a
+ * build that bypassed build.py. */
+const char* afd_source_hash(void);
 
 /*
  * Number of coefficients per node after `level` analysis steps on a length-N signal with an F-tap filter:

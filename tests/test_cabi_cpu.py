@@ -25,7 +25,21 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in _declared_symbols():
         assert hasattr(lib, name), name
-    assert lib.afd_version() >= 100
+    assert lib.afd_version() >= 200
+
+
+def test_library_was_built_from_the_sources_on_disk():
+    """Build provenance: the sha256 of csrc/ + include/afd_b200.h compiled into the binary (afd_source_hash) equals the
+    hash of the sources in the tree -- the prebuilt .so that travels to the GPU box is the committed code."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location(
+        "_afd_build", os.path.join(os.path.dirname(_lib.LIB_PATH), "build.py"))
+    build = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(build)
+    digest = _lib.load().afd_source_hash().decode()
+    assert len(digest) == 64 and digest == build.source_hash() == build.embedded_hash()
 
 
 @pytest.mark.parametrize("N,F,level,T", [(22050, 10, 8, 95), (22050, 24, 8, 109), (22050, 16, 7, 187),
