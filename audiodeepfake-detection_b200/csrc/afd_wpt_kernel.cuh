@@ -33,6 +33,7 @@
 //     first chunk of the CTA's NEXT frame is prefetched while the last level runs.
 #pragma once
 #include <math.h>
+#include <string.h>
 
 #include "afd_common.cuh"
 
@@ -739,6 +740,27 @@ __device__ __forceinline__ void issue_chunk(const float* __restrict__ xg, float*
     cp_async_commit();
 }
 
+// Phase timing (debug builds, -DAFD_WPT_PHASE_TIMING=1): thread 0 of every CTA adds the clock64() span of each
+// barrier-delimited phase to g_wpt_phase[]; launch() prints the table after every launch.  Slots: 0 wait for the staged
+// chunk (cp.async + barrier), 1 level-1 filtering, 2 barrier + copy pass after level 1, 3+pi pass pi (incl. its closing
+// barrier for stored levels; the last level is closed by the next frame's first barrier, i.e. slot 0), 30 frames, 31 total.
+#ifndef AFD_WPT_PHASE_TIMING
+#define AFD_WPT_PHASE_TIMING 0
+#endif
+#if AFD_WPT_PHASE_TIMING
+static __device__ unsigned long long g_wpt_phase[32];
+#define AFD_PHASE_MARK(slot)                                                                       \
+    do {                                                                                           \
+        if (threadIdx.x == 0) {                                                                    \
+            const long long now_ = clock64();                                                      \
+            atomicAdd(&g_wpt_phase[slot], static_cast<unsigned long long>(now_ - phase_t0_));      \
+            phase_t0_ = now_;                                                                      \
+        }                                                                                          \
+    } while (0)
+#else
+#define AFD_PHASE_MARK(slot) do { } while (0)
+#endif
+
 template <int F, int R1, int RA, int RB, int RLA, int RLB, bool LAT, bool EXT>
 __global__ void __launch_bounds__(kThreads, 2)
 wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B, float* __restrict__ out,
@@ -772,6 +794,10 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
     ts.s[0] = ts.s[1] = ts.q[0] = ts.q[1] = ts.m[0] = ts.m[1] = 0.f;
     ts.fs[0] = ts.fs[1] = ts.fq[0] = ts.fq[1] = 0.f;
     ts.col[0] = ts.col[1] = -1;
+#if AFD_WPT_PHASE_TIMING
+    long long phase_t0_ = clock64();
+    const long long phase_start_ = phase_t0_;
+#endif
 
     for (long long wk = blockIdx.x; wk < 2 * B; wk += gridDim.x) {
         const long long b = wk >> 1;
@@ -787,10 +813,12 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
         for (int j = 0; j < plan.nch; ++j) {
             cp_async_wait<0>();
             __syncthreads();
+            AFD_PHASE_MARK(0);
             if (j + 1 < plan.nch) issue_chunk<F>(xg, ((j + 1) & 1) ? buf1 : buf0, j + 1, plan);
             const int kb = j * plan.kc;
             const int ke = min(n1, kb + plan.kc);
             level1_chunk<F, R1, REFL>((j & 1) ? buf1 : buf0, regA, kb, ke, n1, sp1, t1, t1p);
+            AFD_PHASE_MARK(1);
         }
         __syncthreads();
         if constexpr (MirrorCopy<F>::value) {
@@ -799,6 +827,7 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
                 __syncthreads();
             }
         }
+        AFD_PHASE_MARK(2);
         float* out_b = out + b * C * static_cast<long long>(T) * P;
         if (L == 1) {
             // the level-1 node is the output: epilogue straight from shared memory (rare configuration)
@@ -836,6 +865,7 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
                     mirror_copy<F>(smem + ps.out_off, 2 * ps.parents, ps.n_out, ps.out_stride);
                     __syncthreads();
                 }
+                AFD_PHASE_MARK(3 + pi);
             } else {
                 if (ps.prefetch && nb < 2 * B) {
                     issue_chunk<F>(x + (nb >> 1) * x_row_stride, buf0, 0, plan);
@@ -843,9 +873,16 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
                 }
                 if (ps.rsel == 0) last_level<F, RLA, LAT, EXT, REFL>(smem + ps.in_off, ps, T, half_base, out_b, P, cf, ep, ts);
                 else last_level<F, RLB, LAT, EXT, REFL>(smem + ps.in_off, ps, T, half_base, out_b, P, cf, ep, ts);
+                AFD_PHASE_MARK(3 + pi);
             }
         }
+#if AFD_WPT_PHASE_TIMING
+        if (threadIdx.x == 0) atomicAdd(&g_wpt_phase[30], 1ull);
+#endif
     }
+#if AFD_WPT_PHASE_TIMING
+    if (threadIdx.x == 0) atomicAdd(&g_wpt_phase[31], static_cast<unsigned long long>(clock64() - phase_start_));
+#endif
     cp_async_wait<0>();
     if constexpr (EXT) {
         if (ep.node_stats) flush_node_stats(ep, P, ts);   // stats_simple: the one flush of the launch
@@ -994,75 +1031,111 @@ struct PlanReport {
     int pass_r[kMaxPasses];          // item size chosen for each pass
 };
 
+// Everything about a launch that depends only on (device, N, level, taps): planned once and reused.  A training / eval
+// loop calls the transform with the same shape every step, and at small batches (BASELINE configs[0]: 128 frames, a 23 us
+// kernel) the planning, the occupancy query and the attribute calls would otherwise cost several times the kernel.
+template <int F>
+struct LaunchCache {
+    bool valid = false;
+    int dev = -1, L = 0, ctas = 0, sms = 0, stats_simple = 0;
+    int64_t N = 0;
+    double taps[F];
+    WptPlan plan;
+    Coefs<F> cf;
+};
+
 template <int F, int R1, int RA, int RB, int RLA, int RLB, bool LAT, bool EXT>
 static int launch(const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* out, int L,
                   const double* dec_lo, const LatticeInfo& lat, const Epilogue& ep, cudaStream_t stream,
                   PlanReport* report) {
-    WptPlan plan;
-    Tuning tu{R1, RA, RB, RLA, RLB, LAT, LAT ? (F / 2 - 1) * 0.5 : 0.0};
-    int ctas = 2;
-    int rc = make_plan(N, F, L, tu, 2, lat.scale, &plan);
-    if (rc == AFD_ERR_UNSUPPORTED) {
-        ctas = 1;
-        rc = make_plan(N, F, L, tu, 1, lat.scale, &plan);
-        if (rc == AFD_ERR_UNSUPPORTED)
-            return fail(AFD_ERR_UNSUPPORTED,
-                        "wavelet-packet tree (N=%lld, F=%d, level=%d) needs %lld bytes of shared memory per CTA, limit %d",
-                        static_cast<long long>(N), F, L, 4LL * plan.smem_floats, kMaxSmemPerCta);
-    }
-    if (rc != AFD_OK) return rc;
-    if (report) {
-        report->smem_bytes = 4 * plan.smem_floats; report->ctas_per_sm = ctas; report->lattice = LAT ? 1 : 0;
-        report->passes = plan.npass; report->nch = plan.nch; report->kc = plan.kc;
-        for (int i = 0; i < plan.npass; ++i) {
-            const Pass& ps = plan.pass[i];
-            const int r = ps.kind == 0 ? (ps.rsel ? RB : RA) : (ps.rsel ? RLB : RLA);
-            report->pass_r[i] = r;
-            report->pass_items[i] = ps.parents * ((ps.n_out + r - 1) / r);
-        }
-        return AFD_OK;
-    }
-    Coefs<F> cf;
-    for (int k = 0; k < F; ++k) {
-        cf.lo[k] = static_cast<float>(dec_lo[k]);
-        cf.hi[k] = static_cast<float>(((k & 1) ? 1.0 : -1.0) * dec_lo[F - 1 - k]);   // dec_hi[k] = (-1)^(k+1) dec_lo[F-1-k]
-    }
-    for (int m = 0; m < F / 2; ++m) cf.t[m] = LAT ? static_cast<float>(lat.tan_theta[m]) : 0.f;
     auto kern = wpt_tree_kernel<F, R1, RA, RB, RLA, RLB, LAT, EXT>;
-    static thread_local bool configured[16] = {false};  // per device
-    int dev = 0, sms = kNumSmsFallback;
-    AFD_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev >= 16 || !configured[dev]) {
-        AFD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta));
-        AFD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                          cudaSharedmemCarveoutMaxShared));
-        if (dev < 16) configured[dev] = true;
-    }
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (ctas == 2) {
-        // the plan may sit exactly on the two-CTAs-per-SM boundary: if the driver disagrees, re-plan with head-room
-        int resident = 0;
-        AFD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kThreads, 4 * plan.smem_floats));
-        if (resident < 2 && make_plan(N, F, L, tu, 2, lat.scale, &plan, 4096) != AFD_OK) {
+    static thread_local LaunchCache<F> cache;              // one per instantiation and host thread
+    int dev = 0;
+    if (!report) AFD_CUDA_TRY(cudaGetDevice(&dev));
+    if (report || !cache.valid || cache.dev != dev || cache.N != N || cache.L != L ||
+        memcmp(cache.taps, dec_lo, sizeof(double) * F) != 0) {
+        cache.valid = false;
+        WptPlan& plan = cache.plan;
+        Tuning tu{R1, RA, RB, RLA, RLB, LAT, LAT ? (F / 2 - 1) * 0.5 : 0.0};
+        int ctas = 2;
+        int rc = make_plan(N, F, L, tu, 2, lat.scale, &plan);
+        if (rc == AFD_ERR_UNSUPPORTED) {
             ctas = 1;
             rc = make_plan(N, F, L, tu, 1, lat.scale, &plan);
-            if (rc != AFD_OK) return rc;
+            if (rc == AFD_ERR_UNSUPPORTED)
+                return fail(AFD_ERR_UNSUPPORTED,
+                            "wavelet-packet tree (N=%lld, F=%d, level=%d) needs %lld bytes of shared memory per CTA, limit %d",
+                            static_cast<long long>(N), F, L, 4LL * plan.smem_floats, kMaxSmemPerCta);
         }
+        if (rc != AFD_OK) return rc;
+        if (report) {
+            report->smem_bytes = 4 * plan.smem_floats; report->ctas_per_sm = ctas; report->lattice = LAT ? 1 : 0;
+            report->passes = plan.npass; report->nch = plan.nch; report->kc = plan.kc;
+            for (int i = 0; i < plan.npass; ++i) {
+                const Pass& ps = plan.pass[i];
+                const int r = ps.kind == 0 ? (ps.rsel ? RB : RA) : (ps.rsel ? RLB : RLA);
+                report->pass_r[i] = r;
+                report->pass_items[i] = ps.parents * ((ps.n_out + r - 1) / r);
+            }
+            return AFD_OK;
+        }
+        Coefs<F>& cf = cache.cf;
+        for (int k = 0; k < F; ++k) {
+            cf.lo[k] = static_cast<float>(dec_lo[k]);
+            cf.hi[k] = static_cast<float>(((k & 1) ? 1.0 : -1.0) * dec_lo[F - 1 - k]);   // dec_hi[k] = (-1)^(k+1) dec_lo[F-1-k]
+        }
+        for (int m = 0; m < F / 2; ++m) cf.t[m] = LAT ? static_cast<float>(lat.tan_theta[m]) : 0.f;
+        static thread_local bool configured[16] = {false};  // per device
+        int sms = kNumSmsFallback;
+        if (dev >= 16 || !configured[dev]) {
+            AFD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta));
+            AFD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                              cudaSharedmemCarveoutMaxShared));
+            if (dev < 16) configured[dev] = true;
+        }
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (ctas == 2) {
+            // the plan may sit exactly on the two-CTAs-per-SM boundary: if the driver disagrees, re-plan with head-room
+            int resident = 0;
+            AFD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kThreads, 4 * plan.smem_floats));
+            if (resident < 2 && make_plan(N, F, L, tu, 2, lat.scale, &plan, 4096) != AFD_OK) {
+                ctas = 1;
+                rc = make_plan(N, F, L, tu, 1, lat.scale, &plan);
+                if (rc != AFD_OK) return rc;
+            }
+        }
+        {   // derived from the plan that is actually launched (the occupancy fallback above may have re-planned)
+            int last_passes = 0, parents = 0;
+            for (int i = 0; i < plan.npass; ++i)
+                if (plan.pass[i].kind == 1) { ++last_passes; parents = plan.pass[i].parents; }
+            cache.stats_simple = (last_passes == 1 && parents <= kThreads && kThreads % parents == 0) ? 1 : 0;
+        }
+        cache.dev = dev; cache.N = N; cache.L = L; cache.ctas = ctas; cache.sms = sms;
+        memcpy(cache.taps, dec_lo, sizeof(double) * F);
+        cache.valid = true;
     }
     Epilogue epk = ep;
-    {   // derived from the plan that is actually launched (the occupancy fallback above may have re-planned)
-        int last_passes = 0, parents = 0;
-        for (int i = 0; i < plan.npass; ++i)
-            if (plan.pass[i].kind == 1) { ++last_passes; parents = plan.pass[i].parents; }
-        epk.stats_simple = (last_passes == 1 && parents <= kThreads && kThreads % parents == 0) ? 1 : 0;
-    }
-    const int smem = 4 * plan.smem_floats;
-    long long grid = 2LL * sms * ctas / 2 * 2;             // persistent: every resident slot, even count
-    if (ctas == 1) grid = sms / 2 * 2;
+    epk.stats_simple = cache.stats_simple;
+    const int smem = 4 * cache.plan.smem_floats;
+    long long grid = 2LL * cache.sms * cache.ctas / 2 * 2;             // persistent: every resident slot, even count
+    if (cache.ctas == 1) grid = cache.sms / 2 * 2;
     if (grid > 2 * B) grid = 2 * B;
     kern<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(x, static_cast<long long>(x_row_stride),
-                                                                   static_cast<long long>(B), out, plan, cf, epk);
+                                                                   static_cast<long long>(B), out, cache.plan, cache.cf, epk);
     AFD_CUDA_TRY(cudaGetLastError());
+#if AFD_WPT_PHASE_TIMING
+    {
+        unsigned long long h[32];
+        cudaDeviceSynchronize();
+        cudaMemcpyFromSymbol(h, g_wpt_phase, sizeof(h));
+        const double half_frames = static_cast<double>(h[30] ? h[30] : 1);
+        fprintf(stderr, "wpt phases F=%d B=%lld (thread-0 cycles per half frame): ", F, static_cast<long long>(B));
+        for (int i = 0; i < 3 + cache.plan.npass; ++i) fprintf(stderr, "%s%.0f", i ? " " : "", h[i] / half_frames);
+        fprintf(stderr, " | total %.0f\n", h[31] / half_frames);
+        memset(h, 0, sizeof(h));
+        cudaMemcpyToSymbol(g_wpt_phase, h, sizeof(h));
+    }
+#endif
     return AFD_OK;
 }
 
@@ -1080,7 +1153,17 @@ static int dispatch_one(const float* x, int64_t B, int64_t N, int64_t x_row_stri
     LatticeInfo lat{};
     lat.scale = 1.0;
     if constexpr (F <= 32) {
-        if (lattice_factor(dec_lo, F, &lat) == AFD_OK && lat.usable)
+        static thread_local double seen[F];                    // the factorisation of the last taps seen by this thread
+        static thread_local LatticeInfo seen_lat{};
+        static thread_local int seen_rc = -1;
+        if (seen_rc < 0 || memcmp(seen, dec_lo, sizeof(double) * F) != 0) {
+            seen_lat = LatticeInfo{};
+            seen_lat.scale = 1.0;
+            seen_rc = lattice_factor(dec_lo, F, &seen_lat) == AFD_OK ? 1 : 0;
+            memcpy(seen, dec_lo, sizeof(double) * F);
+        }
+        lat = seen_lat;
+        if (seen_rc == 1 && lat.usable)
             return launch<F, pick_r1(F), 22, 26, 14, pick_rlb(F), true, EXT>(x, B, N, x_row_stride, out, L, dec_lo, lat, ep, stream, report);
         return launch<F, pick_r1(F), 14, 10, 14, 10, false, EXT>(x, B, N, x_row_stride, out, L, dec_lo, lat, ep, stream, report);
     } else {

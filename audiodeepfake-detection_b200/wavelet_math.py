@@ -54,9 +54,46 @@ def _as_frames(x: torch.Tensor, what: str) -> torch.Tensor:
 
 
 def wpt_out_len(n: int, filt_len: int, level: int) -> int:
-    out = ctypes.c_int64(0)
-    _lib.check("afd_wpt_out_len", _lib.load().afd_wpt_out_len(n, filt_len, level, ctypes.byref(out)))
-    return out.value
+    """Leaf length after ``level`` analysis steps: ``floor((n + F - 1) / 2)`` iterated (== ``afd_wpt_out_len``; kept on
+    the host because it sits on the per-step path of small batches)."""
+    n, filt_len, level = int(n), int(filt_len), int(level)
+    if n < 1 or filt_len < 2 or filt_len % 2 or level < 0:
+        raise _lib.AfdError("afd_wpt_out_len", -1, "afd_wpt_out_len: bad argument")
+    for _ in range(level):
+        n = (n + filt_len - 1) // 2
+    return n
+
+
+class _SameDevice:
+    """No-op stand-in for ``torch.cuda.device(dev)`` when ``dev`` already is the current device (the usual case:
+    one process per GPU); the real context manager costs two driver calls per step."""
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_SAME_DEVICE = _SameDevice()
+
+
+def _on_device(device: torch.device):
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    return _SAME_DEVICE if index == torch.cuda.current_device() else torch.cuda.device(device)
+
+
+def _c_taps(wav):
+    """``dec_lo`` as a ctypes double array, built once per wavelet object."""
+    arr = getattr(wav, "_afd_c_taps", None)
+    if arr is None:
+        taps = [float(v) for v in wav.dec_lo]
+        arr = (ctypes.c_double * len(taps))(*taps)
+        try:
+            wav._afd_c_taps = arr
+        except AttributeError:          # e.g. pywt.Wavelet instances do not take new attributes
+            pass
+    return arr
 
 
 def _norm_array(norm, channels: int):
@@ -111,8 +148,8 @@ def wavelet_packet_features(pt_data: torch.Tensor, wavelet, max_lev: int = 8, lo
     """
     x = _as_frames(pt_data, "wavelet_packet_features")
     wav = get_wavelet(wavelet)
-    taps = [float(v) for v in wav.dec_lo]
-    F = len(taps)
+    c_taps = _c_taps(wav)
+    F = len(c_taps)
     B, N = x.shape
     T = wpt_out_len(N, F, max_lev)
     C = 2 if (log_scale and loss_less) else 1
@@ -121,7 +158,6 @@ def wavelet_packet_features(pt_data: torch.Tensor, wavelet, max_lev: int = 8, lo
     if not store and node_stats is None and feat_moments is None:
         raise ValueError("store=False needs node_stats or feat_moments to accumulate into")
     out = torch.empty((B, C, T, P), dtype=torch.float32, device=x.device) if store else None
-    c_taps = (ctypes.c_double * F)(*taps)
     order_id = _lib.AFD_ORDER_FREQ if order == "freq" else _lib.AFD_ORDER_NATURAL
     stride = x.stride(0) if B > 1 else N
     out_ptr = ctypes.c_void_p(out.data_ptr()) if store else None
@@ -133,7 +169,7 @@ def wavelet_packet_features(pt_data: torch.Tensor, wavelet, max_lev: int = 8, lo
             raise ValueError(f"{what} must be a contiguous {dtype} tensor of shape {shape} on {x.device}")
         return ctypes.c_void_p(t.data_ptr())
 
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         if not extended:
             rc = _lib.load().afd_wpt_forward(
                 ctypes.c_void_p(x.data_ptr()), B, N, stride, c_taps, F, max_lev, order_id,
@@ -331,7 +367,7 @@ def stft_power_features(x: torch.Tensor, n_fft: int = 511, hop_length: int = 220
     out = torch.empty((B, 1, frames, bins), dtype=torch.float32, device=xf.device) if store else None
     out_ptr = ctypes.c_void_p(out.data_ptr()) if store else None
     stride = xf.stride(0) if B > 1 else N
-    with torch.cuda.device(xf.device):
+    with _on_device(xf.device):
         if norm is None and feat_moments is None:
             rc = _lib.load().afd_stft_power(
                 ctypes.c_void_p(xf.data_ptr()), B, N, stride, n_fft, hop_length, float(power),

@@ -43,7 +43,7 @@ def main():
     for impl in ("tc", "pfa"):
         os.environ["AFD_STFT_IMPL"] = impl
         spec = afd.stft_power_features(xt, 511, 220).cpu().numpy()[:, 0]
-        want = ptwt_like.stft_power_dft64(x[:, 0])
+        want = ptwt_like.stft_power_dft64(x[:, 0]).transpose(0, 2, 1)      # [B, bins, frames] -> [B, frames, bins]
         print(f"sanitize: stft 511/220 impl={impl} rel {rel(spec, want):.2e}", flush=True)
         assert rel(spec, want) < 1e-5
     os.environ.pop("AFD_STFT_IMPL", None)
