@@ -97,6 +97,12 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out_path: 
     for src in SOURCES:
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
         flags = list(extra_flags)
+        only = globals().get("SOURCES_VARIANT_ONLY")
+        if variant and only and src not in only:     # variant builds may recompile a few units only
+            prod = os.path.join(PKG_DIR, "build", src.replace(".cu", ".o"))
+            if os.path.exists(prod):
+                objs.append(prod)
+                continue
         if src == "afd_core.cu":                     # the one unit that carries the provenance string
             flags.append('-DAFD_SOURCE_HASH="%s"' % digest)
         elif (not force and not variant and os.path.exists(obj)

@@ -40,7 +40,10 @@
 namespace afd {
 
 constexpr int kMaxLevel = 12;
-constexpr int kThreads = 256;
+#ifndef AFD_WPT_THREADS
+#define AFD_WPT_THREADS 256
+#endif
+constexpr int kThreads = AFD_WPT_THREADS;
 constexpr int kMaxPasses = 24;
 
 template <int F>
@@ -69,6 +72,7 @@ struct Pass {
     // chunk classification of the child nodes for the chosen item size (make_split, evaluated on the host)
     int C, CL, CIe, CR, NI, NE;
     unsigned magicNI;
+    unsigned magicC;   // floor(i / C) for the uniform item mapping
 };
 
 struct WptPlan {
@@ -264,6 +268,20 @@ constexpr int kMirrorCopyMinF = AFD_WPT_MIRROR_COPY_MINF;
 template <int F>
 struct MirrorCopy {
     static constexpr bool value = AFD_WPT_MIRROR_COPY != 0 && F >= kMirrorCopyMinF;
+};
+// Uniform items (r2): with the left padding gone (ReflOk) the only items that differ from the plain interior item are the
+// ones holding a node's last coefficients: partial chunks (guarded scalar stores) and the right-mirror stores.  A warp that
+// holds one such item runs both store paths back to back and the whole CTA waits for it at the level's barrier (probe
+// tools/probes/phase_overlap.cu: a level of pure items takes 1945 cycles per CTA, the real level 2 with ONE edge item 2733,
+// level 7 with 64 of them 4240).  So every item stores all of its R coefficients with vector stores -- the ones past the
+// node's end are garbage computed from garbage and land in the node's tail space, which the plan sizes for it -- and the
+// right padding is always written by the copy pass that follows the level's barrier.
+#ifndef AFD_WPT_UNIFORM
+#define AFD_WPT_UNIFORM 1
+#endif
+template <int F, bool UNI>
+struct CopyPass {
+    static constexpr bool value = UNI || MirrorCopy<F>::value;
 };
 // With the left padding gone the first chunks of a node are ordinary interior items (lanes along the node, vector stores).
 #ifndef AFD_WPT_REFL_INTERIOR
@@ -507,18 +525,39 @@ __device__ __forceinline__ void scale_all(float (&lo)[R], float (&hi)[R], float 
 }
 
 // Right reflect padding of `nodes` stored nodes of length n: pos[n-1+i] = pos[n-1-i], i = 1 .. F-2 (+1 if n is odd).
+// E = next power of two >= F-1 consecutive threads serve one node (shifts only; lanes walk along the padding).
+__host__ __device__ constexpr int pow2_ge(int v) { int e = 1; while (e < v) e <<= 1; return e; }
 template <int F>
 __device__ __forceinline__ void mirror_copy(float* __restrict__ base, int nodes, int n, int stride) {
     constexpr int padl = F - 2;
-    if constexpr (padl == 0) return;
-    const bool odd = (n & 1) != 0;
-    const int padr = padl + (odd ? 1 : 0);
-    const int total = nodes * padr;
-    for (int idx = threadIdx.x; idx < total; idx += kThreads) {
-        const int node = odd ? idx / (padl + 1) : idx / (padl > 0 ? padl : 1);
-        const int mr = idx - node * padr + 1;
-        float* pos = base + node * stride + padl + (n - 1);
-        pos[mr] = pos[-mr];
+    constexpr int E = pow2_ge(F - 1) < kThreads ? pow2_ge(F - 1) : kThreads;
+    const int padr = padl + (n & 1);
+    if (padr == 0) return;
+    const int e = static_cast<int>(threadIdx.x) & (E - 1);
+    for (int mr = e + 1; mr <= padr; mr += E)                       // one trip unless F - 1 > kThreads
+        for (int node = static_cast<int>(threadIdx.x) / E; node < nodes; node += kThreads / E) {
+            float* pos = base + node * stride + padl + (n - 1);
+            pos[mr] = pos[-mr];
+        }
+}
+
+// One stored tree level with uniform items (see AFD_WPT_UNIFORM): item = (node, chunk), lanes walk along a node.
+template <int F, int R, bool LAT>
+__device__ __forceinline__ void mid_level_uniform(const float* __restrict__ in, float* __restrict__ out, const Pass& ps,
+                                                  const Coefs<F>& cf) {
+    constexpr int padl = F - 2;
+    const int total = ps.parents * ps.C;
+    const bool do_mul = ps.mul != 1.0f;
+    for (int it = threadIdx.x; it < total; it += kThreads) {
+        const int node = fast_div(it, ps.C, ps.magicC);
+        const int c = it - node * ps.C;
+        const int k0 = c * R;
+        float lo[R], hi[R];
+        filter_pair<F, R, LAT, true>(in + node * ps.in_stride + 2 * k0, cf, lo, hi, c == 0, 0);
+        if (do_mul) scale_all<R>(lo, hi, ps.mul);
+        float* d0 = out + (2 * node) * ps.out_stride + padl + k0;
+        vec_store<R>(d0, lo);
+        vec_store<R>(d0 + ps.out_stride, hi);
     }
 }
 
@@ -571,7 +610,7 @@ __device__ __forceinline__ void mid_level(const float* __restrict__ in, float* _
 
 // Level 1 for one staged chunk: outputs [kb, ke) of the CTA's own filter -> padded level-1 node.
 // Sample 2*kb + 2 - F of the (reflect-extended) frame sits at buf[0].
-template <int F, int R, bool REFL>
+template <int F, int R, bool REFL, bool UNI>
 __device__ __forceinline__ void level1_chunk(const float* __restrict__ buf, float* __restrict__ node, int kb, int ke,
                                              int n_out, const Split& sp, const float (&t)[F], const u64 (&t2)[F / 2]) {
     using WN = Win<F, R>;
@@ -586,7 +625,7 @@ __device__ __forceinline__ void level1_chunk(const float* __restrict__ buf, floa
         float y[R];
         if constexpr (AFD_WPT_FFMA2 != 0 && F <= AFD_WPT_PACKED_FIR_MAXF) fir1_packed<F, R>(w, t2, y);
         else fir1<F, R>(w, t, y);
-        if (c >= sp.CL && c < sp.CIe) vec_store<R>(node + padl + k0, y);
+        if (UNI || (c >= sp.CL && c < sp.CIe)) vec_store<R>(node + padl + k0, y);
         else edge_store<R, REFL, MirrorCopy<F>::value>(node, y, k0, n_out, padl);
     }
 }
@@ -769,6 +808,8 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
     extern __shared__ __align__(16) float smem[];
     constexpr int padl = F - 2;
     constexpr bool REFL = ReflOk<F, RA, RB, RLA, RLB>::value;      // left padding by register reflection (see ReflOk)
+    constexpr bool UNI = REFL && AFD_WPT_UNIFORM != 0;               // uniform items + copy pass (see AFD_WPT_UNIFORM)
+    constexpr bool COPY = CopyPass<F, UNI>::value;
     const int L = plan.L;
     const int half = blockIdx.x & 1;                      // gridDim.x is even: constant per CTA
     float* const regA = smem;                              // level-1 node at its start
@@ -817,11 +858,11 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
             if (j + 1 < plan.nch) issue_chunk<F>(xg, ((j + 1) & 1) ? buf1 : buf0, j + 1, plan);
             const int kb = j * plan.kc;
             const int ke = min(n1, kb + plan.kc);
-            level1_chunk<F, R1, REFL>((j & 1) ? buf1 : buf0, regA, kb, ke, n1, sp1, t1, t1p);
+            level1_chunk<F, R1, REFL, UNI>((j & 1) ? buf1 : buf0, regA, kb, ke, n1, sp1, t1, t1p);
             AFD_PHASE_MARK(1);
         }
         __syncthreads();
-        if constexpr (MirrorCopy<F>::value) {
+        if constexpr (COPY) {
             if (L > 1) {
                 mirror_copy<F>(regA, 1, n1, plan.stride1);
                 __syncthreads();
@@ -858,10 +899,15 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
             const Pass& ps = plan.pass[pi];
             if (ps.sync_before) __syncthreads();
             if (ps.kind == 0) {
-                if (ps.rsel == 0) mid_level<F, RA, LAT, REFL>(smem + ps.in_off, smem + ps.out_off, ps, cf);
-                else mid_level<F, RB, LAT, REFL>(smem + ps.in_off, smem + ps.out_off, ps, cf);
+                if constexpr (UNI) {
+                    if (ps.rsel == 0) mid_level_uniform<F, RA, LAT>(smem + ps.in_off, smem + ps.out_off, ps, cf);
+                    else mid_level_uniform<F, RB, LAT>(smem + ps.in_off, smem + ps.out_off, ps, cf);
+                } else {
+                    if (ps.rsel == 0) mid_level<F, RA, LAT, REFL>(smem + ps.in_off, smem + ps.out_off, ps, cf);
+                    else mid_level<F, RB, LAT, REFL>(smem + ps.in_off, smem + ps.out_off, ps, cf);
+                }
                 __syncthreads();
-                if constexpr (MirrorCopy<F>::value) {
+                if constexpr (COPY) {
                     mirror_copy<F>(smem + ps.out_off, 2 * ps.parents, ps.n_out, ps.out_stride);
                     __syncthreads();
                 }
@@ -934,8 +980,18 @@ static int make_plan(int64_t N, int F, int L, const Tuning& tu, int ctas_per_sm,
     const int tail = round_up(2 * maxR + 1, 4);               // over-read slack behind the last node of a region:
                                                               // the last item's window ends <= 2R+1 floats past its node
     const int stored = L == 1 ? 1 : L - 1;                    // levels kept in shared memory
+    const bool uniform = refl_ok && AFD_WPT_UNIFORM != 0;     // == UNI of the launched kernel
     for (int l = 1; l <= stored; ++l) {
         int s = round_up(n[l] + 2 * padl + (n[l] & 1), 4);
+        if (uniform) {
+            // The producer's last chunk stores all of its R coefficients: the node needs R-1 floats of tail space (>= the
+            // right padding).  The left padding is never written and its only reader replaces what it read (ReflOk), so
+            // it aliases the previous node's tail.
+            const int r_prod = l == 1 ? tu.R1 : (tu.RA > tu.RB ? tu.RA : tu.RB);
+            const int padr = padl + (n[l] & 1);
+            const int tail_l = padr > r_prod - 1 ? padr : r_prod - 1;
+            s = round_up(n[l] + (padl > tail_l ? padl : tail_l), 4);
+        }
         if (l >= 2 && ((s >> 2) & 1) == 0) s += 4;            // lanes walk across nodes in edge / last-level items: odd 16-byte stride
         stride[l] = s;
     }
@@ -954,7 +1010,7 @@ static int make_plan(int64_t N, int F, int L, const Tuning& tu, int ctas_per_sm,
         for (int l = 1; l <= stored; ++l) {
             int nodes = 1 << (l - 1);
             if (l == L - 1 && G > 1) nodes /= G;
-            const int fl = nodes * stride[l] + tail;
+            const int fl = nodes * stride[l] + tail + (uniform ? padl : 0);   // aliased left padding: the first node's is extra
             int& r = need[(l & 1) ? 0 : 1];
             r = r > fl ? r : fl;
         }
@@ -973,6 +1029,7 @@ static int make_plan(int64_t N, int F, int L, const Tuning& tu, int ctas_per_sm,
     auto fill_split = [&](Pass& ps, int R) {
         const Split sp = make_split(ps.n_out, R, padl, refl_ok && AFD_WPT_REFL_INTERIOR);
         ps.C = sp.C; ps.CL = sp.CL; ps.CIe = sp.CIe; ps.CR = sp.CR; ps.NI = sp.NI; ps.NE = sp.NE; ps.magicNI = sp.magicNI;
+        ps.magicC = magic_of(sp.C);
     };
     auto stored_mul = [&]() {                                 // factor for a stored level
         if (!tu.lat) return 1.0f;
@@ -1145,7 +1202,17 @@ static int launch(const float* x, int64_t B, int64_t N, int64_t x_row_stride, fl
 constexpr int pick_r1(int F) { return F <= 24 ? 14 : (F <= 40 ? 10 : 6); }
 constexpr int pick_rd(int F) { return F <= 40 ? 10 : 6; }           // direct form, F > 32
 // second last-level item size: a quarter of the leaf length of the headline shape (N = 22050, level 8: T ~ 85 + F)
-constexpr int pick_rlb(int F) { return 2 * ((85 + F + 7) / 8); }
+#ifndef AFD_WPT_RA
+#define AFD_WPT_RA 22
+#define AFD_WPT_RB 26
+#endif
+#ifndef AFD_WPT_RLA
+#define AFD_WPT_RLA 14
+#endif
+#ifndef AFD_WPT_RLB_CHUNKS
+#define AFD_WPT_RLB_CHUNKS 4      // chunks per leaf of the headline shape: 64 parents x 4 chunks = 256 items
+#endif
+constexpr int pick_rlb(int F) { return 2 * ((85 + F + 2 * AFD_WPT_RLB_CHUNKS - 1) / (2 * AFD_WPT_RLB_CHUNKS)); }
 
 template <int F, bool EXT>
 static int dispatch_one(const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* out, int L,
@@ -1164,7 +1231,7 @@ static int dispatch_one(const float* x, int64_t B, int64_t N, int64_t x_row_stri
         }
         lat = seen_lat;
         if (seen_rc == 1 && lat.usable)
-            return launch<F, pick_r1(F), 22, 26, 14, pick_rlb(F), true, EXT>(x, B, N, x_row_stride, out, L, dec_lo, lat, ep, stream, report);
+            return launch<F, pick_r1(F), AFD_WPT_RA, AFD_WPT_RB, AFD_WPT_RLA, pick_rlb(F), true, EXT>(x, B, N, x_row_stride, out, L, dec_lo, lat, ep, stream, report);
         return launch<F, pick_r1(F), 14, 10, 14, 10, false, EXT>(x, B, N, x_row_stride, out, L, dec_lo, lat, ep, stream, report);
     } else {
         return launch<F, pick_r1(F), pick_rd(F), pick_rd(F), pick_rd(F), pick_rd(F), false, EXT>(
