@@ -40,6 +40,8 @@ SIGNATURES = {
                                           c_int, c_int64]),
     "afd_clip_sum_accum": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "afd_rdft_magnitude": (c_int, [c_void_p, c_int64, c_double, c_void_p, c_void_p]),
+    "afd_resample_out_len": (c_int, [c_int64, c_int, c_int, POINTER(c_int64)]),
+    "afd_resample": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p]),
     "afd_wpt_lattice_info": (c_int, [POINTER(c_double), c_int, POINTER(c_double), POINTER(c_double),
                                      POINTER(c_double), POINTER(c_int)]),
     "afd_wpt_plan_info": (c_int, [c_int64, POINTER(c_double), c_int, c_int, POINTER(c_int), POINTER(c_int),

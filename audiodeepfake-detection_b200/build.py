@@ -12,7 +12,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libafd_b200.so")
 SOURCES = ["afd_wpt_g0.cu", "afd_wpt_g1.cu", "afd_wpt_g2.cu", "afd_wpt_g3.cu",
            "afd_wpt_x0.cu", "afd_wpt_x1.cu", "afd_wpt_x2.cu", "afd_wpt_x3.cu", "afd_core.cu", "afd_lattice.cu", "afd_wpt.cu",
-           "afd_stft.cu", "afd_stft_pfa.cu", "afd_stft_tc.cu", "afd_haar.cu", "afd_rfft.cu", "afd_host.cu"]
+           "afd_stft.cu", "afd_stft_pfa.cu", "afd_stft_tc.cu", "afd_haar.cu", "afd_rfft.cu", "afd_resample.cu", "afd_host.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",

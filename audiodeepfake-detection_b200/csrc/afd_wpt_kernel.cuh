@@ -33,6 +33,7 @@
 //     first chunk of the CTA's NEXT frame is prefetched while the last level runs.
 #pragma once
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "afd_common.cuh"
@@ -73,6 +74,8 @@ struct Pass {
     int C, CL, CIe, CR, NI, NE;
     unsigned magicNI;
     unsigned magicC;   // floor(i / C) for the uniform item mapping
+    int in_group_off;  // frame kernel: float offset of group 1's input / output nodes relative to group 0's (each group keeps
+    int out_group_off; // its half tree in its own half of a region: the groups work on different levels at the same time)
 };
 
 struct WptPlan {
@@ -87,6 +90,7 @@ struct WptPlan {
     int nch;                    // staging chunks per frame
     int npass;
     int smem_floats;            // total dynamic shared memory in floats
+    int stagger;                // frame kernel: cycles group 1 idles after level 1 so that the groups run out of phase
     Pass pass[kMaxPasses];
 };
 
@@ -528,14 +532,15 @@ __device__ __forceinline__ void scale_all(float (&lo)[R], float (&hi)[R], float 
 // E = next power of two >= F-1 consecutive threads serve one node (shifts only; lanes walk along the padding).
 __host__ __device__ constexpr int pow2_ge(int v) { int e = 1; while (e < v) e <<= 1; return e; }
 template <int F>
-__device__ __forceinline__ void mirror_copy(float* __restrict__ base, int nodes, int n, int stride) {
+__device__ __forceinline__ void mirror_copy(float* __restrict__ base, int nodes, int n, int stride,
+                                            int tid = threadIdx.x, int nthr = kThreads) {
     constexpr int padl = F - 2;
-    constexpr int E = pow2_ge(F - 1) < kThreads ? pow2_ge(F - 1) : kThreads;
+    constexpr int E = pow2_ge(F - 1) < 128 ? pow2_ge(F - 1) : 128;
     const int padr = padl + (n & 1);
     if (padr == 0) return;
-    const int e = static_cast<int>(threadIdx.x) & (E - 1);
-    for (int mr = e + 1; mr <= padr; mr += E)                       // one trip unless F - 1 > kThreads
-        for (int node = static_cast<int>(threadIdx.x) / E; node < nodes; node += kThreads / E) {
+    const int e = tid & (E - 1);
+    for (int mr = e + 1; mr <= padr; mr += E)                       // one trip (F - 1 <= 128)
+        for (int node = tid / E; node < nodes; node += nthr / E) {
             float* pos = base + node * stride + padl + (n - 1);
             pos[mr] = pos[-mr];
         }
@@ -544,11 +549,11 @@ __device__ __forceinline__ void mirror_copy(float* __restrict__ base, int nodes,
 // One stored tree level with uniform items (see AFD_WPT_UNIFORM): item = (node, chunk), lanes walk along a node.
 template <int F, int R, bool LAT>
 __device__ __forceinline__ void mid_level_uniform(const float* __restrict__ in, float* __restrict__ out, const Pass& ps,
-                                                  const Coefs<F>& cf) {
+                                                  const Coefs<F>& cf, int tid = threadIdx.x, int nthr = kThreads) {
     constexpr int padl = F - 2;
     const int total = ps.parents * ps.C;
     const bool do_mul = ps.mul != 1.0f;
-    for (int it = threadIdx.x; it < total; it += kThreads) {
+    for (int it = tid; it < total; it += nthr) {
         const int node = fast_div(it, ps.C, ps.magicC);
         const int c = it - node * ps.C;
         const int k0 = c * R;
@@ -640,7 +645,7 @@ __device__ __forceinline__ unsigned igray(unsigned x) {
 template <int F, int RL, bool LAT, bool EXT, bool REFL>
 __device__ __forceinline__ void last_level(const float* __restrict__ in, const Pass& ps, int T, int half_base,
                                            float* __restrict__ out_b, int P, const Coefs<F>& cf, const Epilogue& ep,
-                                           ThreadStats& ts) {
+                                           ThreadStats& ts, int tid = threadIdx.x, int nthr = kThreads) {
     const int parents = ps.parents;
     const int chunks = (T + RL - 1) / RL;
     const int total = parents * chunks;
@@ -650,7 +655,7 @@ __device__ __forceinline__ void last_level(const float* __restrict__ in, const P
     const float off = ep.log_offset;
     const long long ch1 = static_cast<long long>(T) * P;
     constexpr bool extended = EXT;                                   // afd_wpt_forward_ex instantiation
-    for (int it = threadIdx.x; it < total; it += kThreads) {
+    for (int it = tid; it < total; it += nthr) {
         const int m = it & (parents - 1);
         const int c = it >> ps.lg_parents;
         const int k0 = c * RL;
@@ -740,7 +745,7 @@ __device__ __forceinline__ void last_level(const float* __restrict__ in, const P
 // Stage chunk j of the frame (with the frame's own reflect padding) into `buf` with cp.async.
 template <int F>
 __device__ __forceinline__ void issue_chunk(const float* __restrict__ xg, float* __restrict__ buf, int j,
-                                            const WptPlan& plan) {
+                                            const WptPlan& plan, const int nthr = kThreads, const int tid_in = -1) {
     const int N = plan.N;
     const int kb = j * plan.kc;
     const int ke = min(plan.n1, kb + plan.kc);
@@ -748,7 +753,7 @@ __device__ __forceinline__ void issue_chunk(const float* __restrict__ xg, float*
     const int s_end = 2 * ke;                     // one past the last sample any stored output needs
     const int r_lo = max(s_start, 0);
     const int r_hi = min(s_end, N);               // real samples [r_lo, r_hi)
-    const int tid = threadIdx.x;
+    const int tid = tid_in >= 0 ? tid_in : static_cast<int>(threadIdx.x);
     {
         // widest copy both addresses allow (a frame is 88,200 B, so odd frames are only 8-byte aligned)
         const char* src = reinterpret_cast<const char*>(xg + r_lo);
@@ -759,23 +764,23 @@ __device__ __forceinline__ void issue_chunk(const float* __restrict__ xg, float*
             const int units = n >> 2;
             const char* s = src + 16 * tid;
             uint32_t d = dst + 16 * tid;
-            for (int i = tid; i < units; i += kThreads, s += 16 * kThreads, d += 16 * kThreads)
+            for (int i = tid; i < units; i += nthr, s += 16 * nthr, d += 16 * nthr)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(s));
             if (tid < (n & 3)) cp_async_4(buf + (r_lo - s_start) + 4 * units + tid, xg + r_lo + 4 * units + tid);
         } else if ((mis & 7) == 0) {
             const int units = n >> 1;
             const char* s = src + 8 * tid;
             uint32_t d = dst + 8 * tid;
-            for (int i = tid; i < units; i += kThreads, s += 8 * kThreads, d += 8 * kThreads)
+            for (int i = tid; i < units; i += nthr, s += 8 * nthr, d += 8 * nthr)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(s));
             if ((n & 1) && tid == 0) cp_async_4(buf + (r_hi - 1 - s_start), xg + r_hi - 1);
         } else {
-            for (int i = r_lo + tid; i < r_hi; i += kThreads) cp_async_4(buf + (i - s_start), xg + i);
+            for (int i = r_lo + tid; i < r_hi; i += nthr) cp_async_4(buf + (i - s_start), xg + i);
         }
     }
     // reflect padding of the frame itself: x~[-i] = x[i], x~[N-1+i] = x[N-1-i]
-    for (int s = s_start + tid; s < 0; s += kThreads) cp_async_4(buf + (s - s_start), xg - s);
-    for (int s = max(N, s_start) + tid; s < s_end; s += kThreads) cp_async_4(buf + (s - s_start), xg + (2 * (N - 1) - s));
+    for (int s = s_start + tid; s < 0; s += nthr) cp_async_4(buf + (s - s_start), xg - s);
+    for (int s = max(N, s_start) + tid; s < s_end; s += nthr) cp_async_4(buf + (s - s_start), xg + (2 * (N - 1) - s));
     cp_async_commit();
 }
 
@@ -932,6 +937,142 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
     cp_async_wait<0>();
     if constexpr (EXT) {
         if (ep.node_stats) flush_node_stats(ep, P, ts);   // stats_simple: the one flush of the launch
+        if (ep.feat_moments) flush_feat_moments(ep, C, ts);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Frame kernel (r2): ONE persistent CTA of 512 threads per frame, for every filter the lattice serves.
+//
+// The two-CTA kernel above splits a frame by level-1 FILTER, so level 1 runs in the direct form (F FMAs per output, the
+// other CTA computes the other channel from its own copy of the frame) and is staged in four barrier-delimited chunks:
+// 21 % (sym5) / 22 % (coif4) of the step.  Here the whole frame is staged ONCE as a padded root node (reflect padding
+// included) and level 1 is an ordinary lattice pass over it -- F FMAs per output PAIR, one round of the 512 threads,
+// half the staging traffic.  From level 2 on the two half trees are independent: thread group g (256 threads) owns the
+// sub-tree under the level-1 node g and synchronises on its own named barrier, so the groups drift apart exactly like the
+// two CTAs did (one group's shared-memory phases overlap the other's FMAs).  The CTA-wide barriers left are the ones
+// around level 1 and the one that frees region B for the prefetch of the next frame while the last level runs.
+// Shared memory: region A = odd levels of the FULL tree, region B = root + even levels (~185 KB sym5, ~215 KB coif4).
+// ------------------------------------------------------------------------------------------------
+#ifndef AFD_WPT_FRAME_KERNEL
+#define AFD_WPT_FRAME_KERNEL 1
+#endif
+#ifndef AFD_WPT_STAGGER_DEFAULT
+#define AFD_WPT_STAGGER_DEFAULT 800
+#endif
+constexpr int kFrameThreads = 512;
+constexpr int kGroupThreads = 256;
+
+__device__ __forceinline__ void group_barrier(int group) {
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kGroupThreads) : "memory");
+}
+
+template <int F, int R0, int RA, int RB, int RLA, int RLB, bool EXT>
+__global__ void __launch_bounds__(kFrameThreads, 1)
+wpt_frame_kernel(const float* __restrict__ x, long long x_row_stride, long long B, float* __restrict__ out,
+                 const __grid_constant__ WptPlan plan, const __grid_constant__ Coefs<F> cf,
+                 const __grid_constant__ Epilogue ep) {
+    extern __shared__ __align__(16) float smem[];
+    static_assert(ReflOk<F, R0, RA, RB, RLA, RLB>::value, "the frame kernel needs register reflection (item sizes >= F/2)");
+    const int L = plan.L;
+    const int tid = threadIdx.x;
+    const int group = tid >> 8;                            // half tree under level-1 node 'a' (0) / 'd' (1)
+    const int gt = tid & (kGroupThreads - 1);
+    float* const root = smem + plan.region_b;              // padded frame: sample i at root[F - 2 + i]
+    const int P = 1 << L;
+    const int C = (ep.log_scale && ep.sign_channel) ? 2 : 1;
+    const int T = plan.T;
+    const int half_base = L >= 2 ? group << (L - 2) : 0;   // natural index of the half tree's first level-(L-1) node
+    bool prefetched = false;
+    bool first = true;
+    // three words behind the planned regions: groups that have finished with region B (monotonic count), and per group
+    // whether it was the second one to arrive
+    unsigned int& s_arrivals = *reinterpret_cast<unsigned int*>(smem + plan.smem_floats);
+    int* const s_second = reinterpret_cast<int*>(smem + plan.smem_floats + 1);
+    if (tid == 0) s_arrivals = 0;
+    ThreadStats ts;
+    ts.s[0] = ts.s[1] = ts.q[0] = ts.q[1] = ts.m[0] = ts.m[1] = 0.f;
+    ts.fs[0] = ts.fs[1] = ts.fq[0] = ts.fq[1] = 0.f;
+    ts.col[0] = ts.col[1] = -1;
+#if AFD_WPT_PHASE_TIMING
+    long long phase_t0_ = clock64();
+    const long long phase_start_ = phase_t0_;
+#endif
+
+    for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+        const float* xg = x + b * x_row_stride;
+        const long long nb = b + gridDim.x;
+        if (!prefetched) {
+            if (!first) __syncthreads();                   // region B may still be read by a group's last passes
+            issue_chunk<F>(xg, root, 0, plan, kFrameThreads);
+        }
+        first = false;
+        prefetched = false;
+        cp_async_wait<0>();
+        __syncthreads();
+        AFD_PHASE_MARK(0);
+        float* out_b = out + b * C * static_cast<long long>(T) * P;
+        // ---------------------------------------------------------------- passes
+        for (int pi = 0; pi < plan.npass; ++pi) {
+            const Pass& ps = plan.pass[pi];
+            if (pi == 0) {
+                // level 1: the root's two children, all 512 threads
+                if (ps.kind == 0) {
+                    mid_level_uniform<F, R0, true>(smem + ps.in_off, smem + ps.out_off, ps, cf, tid, kFrameThreads);
+                    __syncthreads();
+                    mirror_copy<F>(smem + ps.out_off, 2, ps.n_out, ps.out_stride, tid, kFrameThreads);
+                    __syncthreads();
+                    // The barrier leaves both groups in phase: all 16 warps would load, then filter, then store together and
+                    // the shared-memory pipe and the FMA pipe would take turns.  Group 1 idles for a fraction of a pass, so
+                    // that from here on one group's loads / stores overlap the other's FMAs (like two independent CTAs).
+                    if (group == 1 && plan.stagger > 0) {
+                        const long long t0 = clock64();
+                        while (clock64() - t0 < plan.stagger) { }
+                    }
+                } else {
+                    // L == 1: the two leaves straight from the root; group g keeps leaf g
+                    if (ps.prefetch && nb < B) { issue_chunk<F>(x + nb * x_row_stride, root, 0, plan, kFrameThreads); prefetched = true; }
+                    last_level<F, RLA, true, EXT, true>(smem + ps.in_off, ps, T, 0, out_b, P, cf, ep, ts, tid, kFrameThreads);
+                }
+                AFD_PHASE_MARK(1);
+                continue;
+            }
+            // levels >= 2: group g works on the nodes under level-1 node g
+            const float* in = smem + ps.in_off + group * ps.in_group_off;
+            if (ps.kind == 0) {
+                float* o = smem + ps.out_off + group * ps.out_group_off;
+                if (ps.rsel == 0) mid_level_uniform<F, RA, true>(in, o, ps, cf, gt, kGroupThreads);
+                else mid_level_uniform<F, RB, true>(in, o, ps, cf, gt, kGroupThreads);
+                group_barrier(group);
+                mirror_copy<F>(o, 2 * ps.parents, ps.n_out, ps.out_stride, gt, kGroupThreads);
+                group_barrier(group);
+            } else {
+                if (ps.prefetch) {
+                    // Region B (root + even levels) is free once BOTH groups have produced level L-1.  No CTA-wide barrier
+                    // (it would put the groups back in phase): the group that gets here second stages the next frame.
+                    if (gt == 0) s_second[group] = static_cast<int>(atomicAdd(&s_arrivals, 1u) & 1u);
+                    group_barrier(group);
+                    if (nb < B) {
+                        if (s_second[group]) issue_chunk<F>(x + nb * x_row_stride, root, 0, plan, kGroupThreads, gt);
+                        prefetched = true;
+                    }
+                }
+                if (ps.rsel == 0) last_level<F, RLA, true, EXT, true>(in, ps, T, half_base, out_b, P, cf, ep, ts, gt, kGroupThreads);
+                else last_level<F, RLB, true, EXT, true>(in, ps, T, half_base, out_b, P, cf, ep, ts, gt, kGroupThreads);
+            }
+            AFD_PHASE_MARK(1 + pi);
+        }
+#if AFD_WPT_PHASE_TIMING
+        if (threadIdx.x == 0) atomicAdd(&g_wpt_phase[30], 1ull);
+#endif
+    }
+#if AFD_WPT_PHASE_TIMING
+    if (threadIdx.x == 0) atomicAdd(&g_wpt_phase[31], static_cast<unsigned long long>(clock64() - phase_start_));
+#endif
+    cp_async_wait<0>();
+    if constexpr (EXT) {
+        if (ep.node_stats) flush_node_stats(ep, P, ts);
         if (ep.feat_moments) flush_feat_moments(ep, C, ts);
     }
 }
@@ -1196,6 +1337,185 @@ static int launch(const float* x, int64_t B, int64_t N, int64_t x_row_stride, fl
     return AFD_OK;
 }
 
+
+// Plan of the frame kernel: full tree, level l = 2^l nodes (the nodes of half tree g are the contiguous half g), root =
+// the padded frame at the start of region B.  pass[0] is level 1 (all threads); pass[l-1], l >= 2, carries the PER-GROUP
+// parent count and group-0 offsets.  Returns AFD_ERR_UNSUPPORTED when the tree does not fit one CTA.
+static int make_frame_plan(int64_t N, int F, int L, int R0, const Tuning& tu, double level_scale, WptPlan* p) {
+    int n[kMaxLevel + 1], stride[kMaxLevel + 1];
+    p->N = static_cast<int>(N);
+    p->L = L;
+    n[0] = static_cast<int>(N);
+    for (int l = 1; l <= L; ++l) n[l] = (n[l - 1] + F - 1) / 2;
+    for (int l = 0; l < L; ++l)
+        if (n[l] < F - 1 + (n[l] & 1) || n[l] < 2)
+            return fail(AFD_ERR_REFLECT_PAD,
+                        "node length %d at level %d is not longer than the reflect padding of a %d-tap filter",
+                        n[l], l, F);
+    p->n1 = n[1];
+    p->T = n[L];
+    const int padl = F - 2;
+    int maxR = R0;
+    for (int r : {tu.RA, tu.RB, tu.RLA, tu.RLB}) maxR = r > maxR ? r : maxR;
+    const int tail = round_up(2 * maxR + 1, 4);
+    // root: staged by issue_chunk(j = 0) with kc = n1: samples 2 - F .. 2 n1 - 1, over-read by the last item's window
+    p->kc = n[1];
+    p->nch = 1;
+    const int c1 = (n[1] + R0 - 1) / R0;
+    if (c1 > kFrameThreads) return AFD_ERR_UNSUPPORTED;
+    p->buf_floats = round_up(2 * c1 * R0 + F + 8, 4);
+    stride[0] = p->buf_floats;
+    for (int l = 1; l < L; ++l) {
+        const int r_prod = l == 1 ? R0 : (tu.RA > tu.RB ? tu.RA : tu.RB);
+        const int padr = padl + (n[l] & 1);
+        const int tail_l = padr > r_prod - 1 ? padr : r_prod - 1;
+        int s = round_up(n[l] + (padl > tail_l ? padl : tail_l), 4);
+        if (l >= 2 && ((s >> 2) & 1) == 0) s += 4;            // lanes walk across nodes in the last level: odd 16-byte stride
+        stride[l] = s;
+    }
+    // Each group keeps its half tree in its own half of a region: the groups run out of phase, so one group may write
+    // level l + 2 while the other still reads level l of the same region, and the per-level layouts do not nest.
+    int half[2] = {0, 0};                                     // [0] = region A (odd levels), [1] = region B (even levels)
+    for (int l = 1; l < L; ++l) {
+        const int fl = (1 << (l - 1)) * stride[l] + tail + padl;
+        int& r = half[(l & 1) ? 0 : 1];
+        r = r > fl ? r : fl;
+    }
+    half[0] = round_up(half[0], 4);
+    half[1] = round_up(half[1], 4);
+    if (L > 1) stride[1] = half[0];                           // the two level-1 nodes are one group half apart
+    p->stride1 = L > 1 ? stride[1] : 0;
+    const int root_floats = p->buf_floats + tail;
+    p->region_b = 2 * half[0];
+    p->smem_floats = p->region_b + (2 * half[1] > root_floats ? 2 * half[1] : round_up(root_floats, 4));
+    if (4LL * (p->smem_floats + 4) > kMaxSmemPerCta) return AFD_ERR_UNSUPPORTED;      // + the kernel's three sync words
+    auto region = [&](int l) { return (l & 1) ? 0 : p->region_b; };
+    double pending = 1.0;
+    auto stored_mul = [&]() {
+        pending *= level_scale;
+        if (fabs(pending) < 1e-9 || fabs(pending) > 1e9) { const float m = static_cast<float>(pending); pending = 1.0; return m; }
+        return 1.0f;
+    };
+    auto pick = [&](int nodes, int n_out, int ra, int rb) {
+        return level_cost(nodes, n_out, rb, tu.halo) < level_cost(nodes, n_out, ra, tu.halo) ? 1 : 0;
+    };
+    int np = 0;
+    for (int l = 1; l < L; ++l) {
+        Pass& ps = p->pass[np++];
+        ps = Pass{};
+        ps.kind = 0; ps.in_off = region(l - 1); ps.out_off = region(l);
+        ps.parents = l == 1 ? 1 : 1 << (l - 2);               // per group from level 2 on
+        ps.lg_parents = l == 1 ? 0 : l - 2;
+        ps.n_out = n[l]; ps.n_in = n[l - 1];
+        ps.in_stride = stride[l - 1]; ps.out_stride = stride[l];
+        ps.in_group_off = l == 1 ? 0 : half[((l - 1) & 1) ? 0 : 1];
+        ps.out_group_off = half[(l & 1) ? 0 : 1];
+        ps.rsel = l == 1 ? 0 : pick(ps.parents, ps.n_out, tu.RA, tu.RB);
+        const int R = l == 1 ? R0 : (ps.rsel ? tu.RB : tu.RA);
+        ps.mul = stored_mul();
+        ps.C = (ps.n_out + R - 1) / R;
+        ps.magicC = magic_of(ps.C);
+        if (l >= 2 && ps.parents * ps.C > 4 * kGroupThreads) return AFD_ERR_UNSUPPORTED;   // degenerate shapes: old kernel
+    }
+    Pass& ps = p->pass[np++];
+    ps = Pass{};
+    ps.kind = 1; ps.in_off = region(L - 1);
+    ps.parents = L == 1 ? 1 : 1 << (L - 2); ps.lg_parents = L == 1 ? 0 : L - 2;
+    ps.n_out = n[L]; ps.n_in = n[L - 1];
+    ps.in_stride = stride[L - 1];
+    ps.in_group_off = L == 1 ? 0 : half[((L - 1) & 1) ? 0 : 1];
+    ps.rsel = L == 1 ? 0 : pick(ps.parents, n[L], tu.RLA, tu.RLB);
+    ps.mul = static_cast<float>(pending * level_scale);
+    ps.parent_base = 0;
+    ps.prefetch = ((L - 1) & 1) == 1 ? 1 : 0;                 // region B (root) is idle while the last level reads region A
+    p->npass = np;
+    return AFD_OK;
+}
+
+template <int F, int R0, int RA, int RB, int RLA, int RLB, bool EXT>
+static int launch_frame(const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* out, int L,
+                        const double* dec_lo, const LatticeInfo& lat, const Epilogue& ep, cudaStream_t stream,
+                        PlanReport* report, bool* taken) {
+    auto kern = wpt_frame_kernel<F, R0, RA, RB, RLA, RLB, EXT>;
+    static thread_local LaunchCache<F> cache;
+    static thread_local int cache_ok = 0;                  // 1: plan fits, -1: shape not served by this kernel
+    int dev = 0;
+    *taken = false;
+    if (!report) AFD_CUDA_TRY(cudaGetDevice(&dev));
+    if (report || !cache.valid || cache.dev != dev || cache.N != N || cache.L != L ||
+        memcmp(cache.taps, dec_lo, sizeof(double) * F) != 0) {
+        cache.valid = false;
+        Tuning tu{R0, RA, RB, RLA, RLB, true, (F / 2 - 1) * 0.5};
+        const int rc = make_frame_plan(N, F, L, R0, tu, lat.scale, &cache.plan);
+        if (rc == AFD_ERR_UNSUPPORTED) cache_ok = -1;
+        else if (rc != AFD_OK) return rc;
+        else cache_ok = 1;
+        if (report) {
+            if (cache_ok < 0) return AFD_OK;
+            const WptPlan& plan = cache.plan;
+            report->smem_bytes = 4 * plan.smem_floats; report->ctas_per_sm = 1; report->lattice = 1;
+            report->passes = plan.npass; report->nch = 1; report->kc = plan.kc;
+            for (int i = 0; i < plan.npass; ++i) {
+                const Pass& ps = plan.pass[i];
+                const int r = i == 0 && ps.kind == 0 ? R0 : (ps.kind == 0 ? (ps.rsel ? RB : RA) : (ps.rsel ? RLB : RLA));
+                report->pass_r[i] = r;
+                report->pass_items[i] = ps.parents * ((ps.n_out + r - 1) / r);
+            }
+            *taken = true;
+            return AFD_OK;
+        }
+        if (cache_ok > 0) {
+            const char* stg = getenv("AFD_WPT_STAGGER");  // tuning knob (cycles); default measured on B200
+            cache.plan.stagger = stg ? atoi(stg) : AFD_WPT_STAGGER_DEFAULT;
+            Coefs<F>& cf = cache.cf;
+            for (int k = 0; k < F; ++k) {
+                cf.lo[k] = static_cast<float>(dec_lo[k]);
+                cf.hi[k] = static_cast<float>(((k & 1) ? 1.0 : -1.0) * dec_lo[F - 1 - k]);
+            }
+            for (int m = 0; m < F / 2; ++m) cf.t[m] = static_cast<float>(lat.tan_theta[m]);
+            static thread_local bool configured[16] = {false};
+            if (dev >= 16 || !configured[dev]) {
+                AFD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta));
+                AFD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                  cudaSharedmemCarveoutMaxShared));
+                if (dev < 16) configured[dev] = true;
+            }
+            int sms = kNumSmsFallback;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const int parents = cache.plan.pass[cache.plan.npass - 1].parents;
+            cache.stats_simple = (L >= 2 && parents <= kGroupThreads && kGroupThreads % parents == 0) ? 1 : 0;
+            cache.sms = sms;
+        }
+        cache.dev = dev; cache.N = N; cache.L = L;
+        memcpy(cache.taps, dec_lo, sizeof(double) * F);
+        cache.valid = true;
+    }
+    if (cache_ok < 0) return AFD_OK;                       // not taken: the caller falls back to the two-CTA kernel
+    *taken = true;
+    Epilogue epk = ep;
+    epk.stats_simple = cache.stats_simple;
+    long long grid = cache.sms;
+    if (grid > B) grid = B;
+    kern<<<static_cast<unsigned>(grid), kFrameThreads, 4 * (cache.plan.smem_floats + 4), stream>>>(
+        x, static_cast<long long>(x_row_stride), static_cast<long long>(B), out, cache.plan, cache.cf, epk);
+    AFD_CUDA_TRY(cudaGetLastError());
+#if AFD_WPT_PHASE_TIMING
+    {
+        unsigned long long h[32];
+        cudaDeviceSynchronize();
+        cudaMemcpyFromSymbol(h, g_wpt_phase, sizeof(h));
+        const double frames = static_cast<double>(h[30] ? h[30] : 1);
+        fprintf(stderr, "wpt frame-kernel phases F=%d B=%lld (thread-0 cycles per frame: wait, level 1, level 2, ...): ", F,
+                static_cast<long long>(B));
+        for (int i = 0; i < 1 + cache.plan.npass; ++i) fprintf(stderr, "%s%.0f", i ? " " : "", h[i] / frames);
+        fprintf(stderr, " | total %.0f\n", h[31] / frames);
+        memset(h, 0, sizeof(h));
+        cudaMemcpyToSymbol(g_wpt_phase, h, sizeof(h));
+    }
+#endif
+    return AFD_OK;
+}
+
 // Item sizes.  R/2 odd keeps the 128-bit window loads and 64-bit stores of consecutive lanes conflict-free; larger
 // R amortises the F-2 halo (and, for the lattice, its (J-1)/2 extra rotation columns), smaller R bounds the
 // register window of 2R+F-2 floats.  Two sizes per kernel let the plan fill whole rounds of 256 threads.
@@ -1208,6 +1528,9 @@ constexpr int pick_rd(int F) { return F <= 40 ? 10 : 6; }           // direct fo
 #endif
 #ifndef AFD_WPT_RLA
 #define AFD_WPT_RLA 14
+#endif
+#ifndef AFD_WPT_R0
+#define AFD_WPT_R0 22             // level-1 item size of the frame kernel: 11029 / 22 = 502 items = one round of 512 threads
 #endif
 #ifndef AFD_WPT_RLB_CHUNKS
 #define AFD_WPT_RLB_CHUNKS 4      // chunks per leaf of the headline shape: 64 parents x 4 chunks = 256 items
@@ -1230,8 +1553,16 @@ static int dispatch_one(const float* x, int64_t B, int64_t N, int64_t x_row_stri
             memcpy(seen, dec_lo, sizeof(double) * F);
         }
         lat = seen_lat;
-        if (seen_rc == 1 && lat.usable)
+        if (seen_rc == 1 && lat.usable) {
+            if constexpr (AFD_WPT_FRAME_KERNEL != 0 && AFD_WPT_UNIFORM != 0 && AFD_WPT_THREADS == 256 &&
+                          ReflOk<F, AFD_WPT_R0, AFD_WPT_RA, AFD_WPT_RB, AFD_WPT_RLA, pick_rlb(F)>::value) {
+                bool taken = false;
+                const int rc = launch_frame<F, AFD_WPT_R0, AFD_WPT_RA, AFD_WPT_RB, AFD_WPT_RLA, pick_rlb(F), EXT>(
+                    x, B, N, x_row_stride, out, L, dec_lo, lat, ep, stream, report, &taken);
+                if (rc != AFD_OK || taken) return rc;
+            }
             return launch<F, pick_r1(F), AFD_WPT_RA, AFD_WPT_RB, AFD_WPT_RLA, pick_rlb(F), true, EXT>(x, B, N, x_row_stride, out, L, dec_lo, lat, ep, stream, report);
+        }
         return launch<F, pick_r1(F), 14, 10, 14, 10, false, EXT>(x, B, N, x_row_stride, out, L, dec_lo, lat, ep, stream, report);
     } else {
         return launch<F, pick_r1(F), pick_rd(F), pick_rd(F), pick_rd(F), pick_rd(F), false, EXT>(

@@ -174,6 +174,18 @@ int afd_clip_sum_accum(const float* x, int64_t B, int64_t N, int64_t x_row_strid
 int afd_rdft_magnitude(const double* x, int64_t N, double scale, double* mag, void* stream);
 
 /*
+ * Sample-rate conversion in front of the frame cutter.
+ * Replaces: torchaudio.functional.resample(audio, sample_rate, self.resample_rate)  (src/audiofakedetect/data_loader.py:341-344;
+ *           torchaudio defaults: sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99) -- the polyphase FIR of torchaudio's
+ *           _get_sinc_resample_kernel / _apply_sinc_resample_kernel with the tap table built once per (orig, new) pair.
+ *   x    device fp32 [B][n_in] (row stride x_row_stride);  out  device fp32 [B][n_out] (row stride out_row_stride),
+ *   n_out = ceil(new * n_in / orig) after reducing the rates by their gcd (afd_resample_out_len).  B <= 65535 rows per call.
+ */
+int afd_resample_out_len(int64_t n_in, int orig_freq, int new_freq, int64_t* n_out);
+int afd_resample(const float* x, int64_t B, int64_t n_in, int64_t x_row_stride, int orig_freq, int new_freq,
+                 float* out, int64_t out_row_stride, void* stream);
+
+/*
  * Diagnostic: the paraunitary lattice (plane rotations + unit delays) the wavelet-packet kernel evaluates instead
  * of the direct-form filter pair when `usable` is 1 -- half the multiplies per coefficient pair.  tan_theta
  * receives F/2 stage tangents (stage 0 first), scale the product of the stage cosines, residual the largest

@@ -140,7 +140,9 @@ def test_lattice_factorisation_reproduces_the_filter_pair(name):
     assert np.max(np.abs(hi - np.asarray(dec_hi(taps)))) < 2e-9
 
 
-def test_plan_info_headline_shapes_fit_two_ctas_per_sm():
+def test_plan_info_headline_shapes_fit_one_frame_cta():
+    """Headline shapes run the frame kernel: one 512-thread CTA per frame, every level one round of its threads
+    (level 1: the 512 threads, levels >= 2: the 256 threads of each half-tree group)."""
     from audiodeepfake_detection_b200.wavelets import Wavelet
 
     lib = _lib.load()
@@ -151,6 +153,7 @@ def test_plan_info_headline_shapes_fit_two_ctas_per_sm():
         items, rs = (ctypes.c_int * 24)(), (ctypes.c_int * 24)()
         assert lib.afd_wpt_plan_info(22050, c_taps, len(taps), 8, ctypes.byref(smem), ctypes.byref(ctas),
                                      ctypes.byref(lat), ctypes.byref(npass), items, rs) == 0
-        assert ctas.value == 2 and lat.value == 1 and smem.value <= 115712
-        assert npass.value == 7                                     # levels 2..8, no slicing of level 7
-        assert all(0 < items[i] <= 256 for i in range(npass.value))  # one round of the 256 threads per level
+        assert ctas.value == 1 and lat.value == 1 and smem.value <= 232448
+        assert npass.value == 8                                     # levels 1..8
+        assert 256 < items[0] <= 512                                # level 1: one round of the whole CTA
+        assert all(0 < items[i] <= 256 for i in range(1, npass.value))  # one round of a group's 256 threads per level

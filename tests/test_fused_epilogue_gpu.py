@@ -41,6 +41,8 @@ def _last_level_passes(N, name, level):
     _lib.check("afd_wpt_plan_info", _lib.load().afd_wpt_plan_info(
         N, c_taps, len(taps), level, ctypes.byref(smem), ctypes.byref(ctas), ctypes.byref(lat), ctypes.byref(passes),
         items, rs))
+    if ctas.value == 1 and passes.value == level:      # frame kernel: one pass per level, level 1 included
+        return 1
     return passes.value - max(level - 2, 0)
 
 

@@ -53,3 +53,18 @@ x = torch.from_numpy(np.stack(frames[:4]).astype(np.float32) / 32768.0).unsqueez
 spec = Spectrogram(n_fft=511, hop_length=220, power=2.0)(x)
 np.savez_compressed(os.path.join(OUT, "stft_torchaudio.npz"), power=spec.numpy(), log=torch.log(spec + 1e-12).numpy())
 print("stft", tuple(spec.shape))
+
+# resample_torchaudio.npz -- outputs of torchaudio.functional.resample (the reference's call at data_loader.py:341-344) for
+# the file rates the reference's datasets come in (LJSpeech 22.05 kHz needs none; JSUT 48 kHz, ASVspoof 16 kHz is rejected,
+# 44.1 / 24 kHz vocoders): seeded noise + a chirp, short enough to commit.
+import torchaudio.functional as AF  # noqa: E402
+rng = np.random.default_rng(7)
+res = {}
+for orig in (44100, 48000, 24000, 32000):
+    n = orig // 8 + 37
+    tt = np.arange(n) / orig
+    sig = (0.3 * rng.standard_normal((2, n)) + 0.5 * np.sin(2 * np.pi * (200 + 3000 * tt) * tt)).astype(np.float32)
+    res[f"x_{orig}"] = sig
+    res[f"y_{orig}"] = AF.resample(torch.from_numpy(sig), orig, 22050).numpy()
+np.savez_compressed(os.path.join(OUT, "resample_torchaudio.npz"), **res)
+print("resample", {k: v.shape for k, v in res.items()})
