@@ -14,6 +14,8 @@
 // all clips the CTA processes (thread t always meets the same nodes because the thread count divides 2^(L-1));
 // one double-precision atomicAdd per packet and CTA publishes them at the end.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "afd_common.cuh"
 
@@ -333,6 +335,291 @@ haar_fast_kernel(const float* __restrict__ x, long long x_row_stride, long long 
     if (since_flush) flush();
 }
 
+// ================================================================================================
+// Streaming variant of the fast path (r2): ONE persistent CTA of 512 threads per SM, TWO clip buffers, ONE CTA-wide barrier
+// per clip.  The fast kernel above runs load -> pass A -> pass B -> pass C in lock step (three barriers per clip, every warp
+// in the same phase: the shared-memory pipe and the adders take turns; ncu: 42 % issue utilisation, 18 % barrier stalls, 23 %
+// of the samples in the load region).  Here
+//   * passes A and B of a 32-row block need only that block: the warp that owns block b stages its 4 KB itself (its own
+//     cp.async group), runs pass A on its rows and pass B on the same 32 x 32 tile with __syncwarp() in between;
+//   * pass C of clip n (reads the whole buffer) and the staging + passes A/B of clip n+1 (other buffer) happen in the SAME
+//     barrier interval, every warp at its own pace: loads are in flight during pass C, and one warp's butterflies overlap
+//     another warp's shared-memory traffic;
+//   * the copies are issued by a few LOADER warps that do nothing else: 88 KB of cp.async per clip exceed what an SM keeps in
+//     flight, so the issuing warp blocks in the LSU queue for most of the transfer (phase timing of a first version in
+//     which every warp staged its own blocks: 5.2 k of 10.7 k cycles per clip spent issuing).  Completion is signalled per
+//     block through an mbarrier (cp.async.mbarrier.arrive.noinc) that the block's worker warp waits on;
+//   * blocks (2.4 cost units) and pass-C node groups (1 unit) are dealt to the worker warps by a host-side greedy schedule.
+// Same layout, same butterflies and the same per-thread accumulation order over the clips of a CTA as the fast kernel.
+// ================================================================================================
+#ifndef AFD_HAAR_LOADER_WARPS
+#define AFD_HAAR_LOADER_WARPS 4
+#endif
+#ifndef AFD_HAAR_PHASE_TIMING
+#define AFD_HAAR_PHASE_TIMING 0
+#endif
+#if AFD_HAAR_PHASE_TIMING
+static __device__ unsigned long long g_haar_phase[8];
+#define AFD_HAAR_MARK(slot)                                                                          \
+    do {                                                                                             \
+        if (lane == 0 && (warp == 0 || warp == 15)) {                                                \
+            const long long now_ = clock64();                                                        \
+            atomicAdd(&g_haar_phase[(slot) + (warp ? 4 : 0)], static_cast<unsigned long long>(now_ - t0_)); \
+            t0_ = now_;                                                                              \
+        }                                                                                            \
+    } while (0)
+#else
+#define AFD_HAAR_MARK(slot) do { } while (0)
+#endif
+constexpr int kStreamThreads = 512;
+constexpr int kStreamWarps = kStreamThreads / 32;
+constexpr int kLoaderWarps = AFD_HAAR_LOADER_WARPS;      // warps that only issue the cp.async of the next clip
+constexpr int kWorkerWarps = kStreamWarps - kLoaderWarps;
+constexpr int kMaxBlocksPerWarp = 4;      // n10 <= 64 blocks
+constexpr int kMaxGroupsPerWarp = 3;      // 32 node groups of 32 level-10 nodes over the worker warps (>= 11)
+
+struct HaarStreamPlan {
+    HaarFastPlan fast;
+    int ext_block;                                    // block that holds the appended samples / level-5 elements
+    signed char blocks[kStreamWarps][kMaxBlocksPerWarp];   // -1: none
+    signed char groups[kStreamWarps][kMaxGroupsPerWarp];
+};
+
+template <int K>
+__global__ void __launch_bounds__(kStreamThreads, 1)
+haar_stream_kernel(const float* __restrict__ x, long long x_row_stride, long long B, double* __restrict__ sums,
+                   const __grid_constant__ HaarStreamPlan sp) {
+    extern __shared__ __align__(16) float smem_h[];
+    constexpr int BLK = 1 << K;
+    const HaarFastPlan& plan = sp.fast;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int n5 = plan.n5, n10 = plan.n10, N = plan.N;
+    float acc[kMaxGroupsPerWarp][BLK];
+#pragma unroll
+    for (int q = 0; q < kMaxGroupsPerWarp; ++q)
+#pragma unroll
+        for (int c = 0; c < BLK; ++c) acc[q][c] = 0.f;
+
+    auto flush = [&]() {
+#pragma unroll
+        for (int q = 0; q < kMaxGroupsPerWarp; ++q) {
+            const int g = sp.groups[warp][q];
+            if (g < 0) continue;
+            const unsigned o = static_cast<unsigned>(32 * g + lane);       // level-10 node (LSB-first path)
+#pragma unroll
+            for (int c = 0; c < BLK; ++c) {
+                const unsigned node = o + (static_cast<unsigned>(c) << 10);
+                const unsigned nat = bitrev(node, plan.L);
+                unsigned p = nat;
+                for (int sft = 1; sft < plan.L; sft <<= 1) p ^= p >> sft;
+                atomicAdd(sums + p, static_cast<double>(acc[q][c]) * static_cast<double>(plan.final_scale));
+                acc[q][c] = 0.f;
+            }
+        }
+    };
+
+    // Staging of block b (samples [1024 b, 1024 b + 1024), rows 32 b .. 32 b + 31 of the padded layout) by a loader warp:
+    // cp.async of the widest size the clip's alignment allows (a clip is 88,200 B: odd clips are only 8-byte aligned), then
+    // every lane arrives on the block's mbarrier when its copies have landed.  (Measured alternatives: one TMA bulk copy per
+    // 128-byte row -- the rows are 144 bytes apart in the padded layout -- costs ~95 cycles per copy and is 2.9x slower.)
+    auto stage_block = [&](float* buf, uint32_t bar, const float* xg, int b) {
+        const int s0 = 1024 * b;
+        const unsigned mis = static_cast<unsigned>(reinterpret_cast<uintptr_t>(xg));
+        if ((mis & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = 256 * b + 32 * j + lane;                     // float4 index in the clip
+                if (4 * i + 3 < N) cp_async_16(buf + 4 * i + ((i >> 3) << 2), xg + 4 * i);
+            }
+            const int tail0 = N & ~3;                                      // the clip's last 1 .. 3 samples
+            if (tail0 >= s0 && tail0 < s0 + 1024 && lane < (N & 3)) { const int s = tail0 + lane; cp_async_4(buf + s + ((s >> 5) << 2), xg + s); }
+        } else if ((mis & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int i = 512 * b + 32 * j + lane;                     // float2 index
+                if (2 * i + 1 < N) cp_async_8(buf + 2 * i + ((i >> 4) << 2), xg + 2 * i);
+            }
+            if ((N & 1) && N - 1 >= s0 && N - 1 < s0 + 1024 && lane == 0) { const int s = N - 1; cp_async_4(buf + s + ((s >> 5) << 2), xg + s); }
+        } else {
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) {
+                const int s = s0 + 32 * j + lane;
+                if (s < N) cp_async_4(buf + s + ((s >> 5) << 2), xg + s);
+            }
+        }
+        if (b == sp.ext_block && lane < plan.extA) { const int s = N + lane; cp_async_4(buf + s + ((s >> 5) << 2), xg + plan.tabA[lane]); }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+    };
+
+    // passes A and B of block b, in place, by the warp that staged it
+    auto pass_ab = [&](float* buf, int b, int) {
+        const int r = 32 * b + lane;                        // pass A: lane = row
+        if (r < n5) {
+            float v[32];
+            {
+                const float4* row = reinterpret_cast<const float4*>(buf + 36 * r);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 q4 = row[u];
+                    v[4 * u] = q4.x; v[4 * u + 1] = q4.y; v[4 * u + 2] = q4.z; v[4 * u + 3] = q4.w;
+                }
+            }
+            haar_stage<1>(v); haar_stage<2>(v); haar_stage<4>(v); haar_stage<8>(v); haar_stage<16>(v);
+            float4* row = reinterpret_cast<float4*>(buf + 36 * r);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) row[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+            if (b == sp.ext_block) {                        // this element may be the source of an appended level-5 element
+                for (int e = 0; e < plan.extB; ++e)
+                    if (plan.tabB[e] == r) {
+                        float4* dst = reinterpret_cast<float4*>(buf + 36 * (n5 + e));
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) dst[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                    }
+            }
+        }
+        __syncwarp();
+        {                                                   // pass B: lane = level-5 node, the block's 32 elements
+            float v[32];
+            float* base = buf + lane + 1152 * b;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = base[36 * j];
+            haar_stage<1>(v); haar_stage<2>(v); haar_stage<4>(v); haar_stage<8>(v); haar_stage<16>(v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) base[36 * j] = v[j];
+        }
+    };
+
+    float* const buf0 = smem_h;
+    float* const buf1 = smem_h + plan.buf_floats;
+    // per buffer and block: an mbarrier that completes when the loader warp's copies of that block have landed
+    const uint32_t mbar0 = static_cast<uint32_t>(__cvta_generic_to_shared(smem_h + 2 * plan.buf_floats));
+    auto mbar = [&](int bufi, int b) { return mbar0 + 8u * static_cast<uint32_t>(bufi * (kStreamWarps * kMaxBlocksPerWarp) + b); };
+    if (tid < 2 * n10) {
+        const uint32_t a = mbar(tid / n10, tid % n10);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(32));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const bool loader = warp >= kWorkerWarps;
+    // loader warp l stages blocks l, l + 2, ... of a clip
+    auto load_clip = [&](float* buf, int bufi, const float* xg) {
+        for (int b = warp - kWorkerWarps; b < n10; b += kLoaderWarps) stage_block(buf, mbar(bufi, b), xg, b);
+    };
+    auto shift_of = [&](const float* xg) { return (static_cast<unsigned>(reinterpret_cast<uintptr_t>(xg)) & 15u) ? 2 : 0; };
+    auto wait_block = [&](int bufi, int b, uint32_t parity) {
+        const uint32_t a = mbar(bufi, b);
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        }
+    };
+    int cur = 0;
+    int since_flush = 0;
+    long long it = 0;                                       // clips this CTA has started: buffer it & 1, use it >> 1
+    if (blockIdx.x < B) {
+        const float* xg = x + blockIdx.x * x_row_stride;
+        if (loader) load_clip(buf0, 0, xg);
+        else {
+#pragma unroll
+            for (int t = 0; t < kMaxBlocksPerWarp; ++t)
+                if (sp.blocks[warp][t] >= 0) { wait_block(0, sp.blocks[warp][t], 0); pass_ab(buf0, sp.blocks[warp][t], shift_of(xg)); }
+        }
+    }
+    __syncthreads();
+#if AFD_HAAR_PHASE_TIMING
+    long long t0_ = clock64();
+#endif
+    for (long long clip = blockIdx.x; clip < B; clip += gridDim.x, cur ^= 1, ++it) {
+        float* const buf = cur ? buf1 : buf0;
+        float* const nbuf = cur ? buf0 : buf1;
+        const bool more = clip + gridDim.x < B;
+        if (loader) {
+            // the other buffer's pass C ended before the last barrier
+            if (more) load_clip(nbuf, cur ^ 1, x + (clip + gridDim.x) * x_row_stride);
+            AFD_HAAR_MARK(0);
+        } else {
+            // ---- pass C of this clip: levels 11-L, lane = level-10 node of one of the warp's groups; |c| accumulates in registers
+#pragma unroll
+            for (int q = 0; q < kMaxGroupsPerWarp; ++q) {
+                const int g = sp.groups[warp][q];
+                if (g < 0) continue;
+                const int o = 32 * g + lane;
+                const float* base = buf + o + ((o >> 5) << 2);            // element i of node o sits at base + 1152 i
+                for (int b = 0; b < plan.nL; ++b) {
+                    float v[16];
+                    const bool redirect = (b + 1) * BLK > n10;
+#pragma unroll
+                    for (int j = 0; j < BLK; ++j) {
+                        int i = b * BLK + j;
+                        if (redirect && i >= n10) i = plan.tabC[i - n10];
+                        v[j] = base[1152 * i];
+                    }
+                    if (K >= 1) haar_stage16<1>(v);
+                    if (K >= 2) haar_stage16<2>(v);
+                    if (K >= 3) haar_stage16<4>(v);
+                    if (K >= 4) haar_stage16<8>(v);
+#pragma unroll
+                    for (int c = 0; c < BLK; ++c) acc[q][c] += fabsf(v[c]);
+                }
+            }
+            if (++since_flush == kFlushEvery) { flush(); since_flush = 0; }
+            AFD_HAAR_MARK(0);
+            // ---- passes A and B of the next clip's blocks, each as soon as its copies have landed
+            if (more) {
+                const uint32_t parity = static_cast<uint32_t>(((it + 1) >> 1) & 1);
+                const int nsh = shift_of(x + (clip + gridDim.x) * x_row_stride);
+#pragma unroll
+                for (int t = 0; t < kMaxBlocksPerWarp; ++t)
+                    if (sp.blocks[warp][t] >= 0) { wait_block(cur ^ 1, sp.blocks[warp][t], parity); pass_ab(nbuf, sp.blocks[warp][t], nsh); }
+            }
+        }
+        AFD_HAAR_MARK(2);
+        __syncthreads();
+        AFD_HAAR_MARK(3);
+    }
+    if (since_flush) flush();
+}
+
+// Greedy schedule: blocks (cost 2.4) then node groups (cost 1) to the least loaded warp.
+static bool make_stream_plan(const HaarFastPlan& fp, HaarStreamPlan* sp) {
+    sp->fast = fp;
+    if (fp.n10 > kWorkerWarps * kMaxBlocksPerWarp) return false;
+    sp->ext_block = (fp.n5 - 1) >> 5;
+    if (fp.extA > 32 || ((fp.N + fp.extA - 1) >> 10) != sp->ext_block || (fp.N >> 10) != sp->ext_block) return false;
+    for (int e = 0; e < fp.extB; ++e)
+        if ((fp.tabB[e] >> 5) != sp->ext_block || ((fp.n5 + e) >> 5) != sp->ext_block) return false;
+    for (int e = 0; e < fp.extA; ++e)
+        if ((fp.tabA[e] >> 10) != sp->ext_block) return false;     // appended samples are copied inside their block
+    double load[kStreamWarps] = {0};
+    int nb[kStreamWarps] = {0}, ng[kStreamWarps] = {0};
+    for (int w = kWorkerWarps; w < kStreamWarps; ++w) { nb[w] = kMaxBlocksPerWarp; ng[w] = kMaxGroupsPerWarp; }   // loader warps take no work
+    for (int w = 0; w < kStreamWarps; ++w) {
+        for (int t = 0; t < kMaxBlocksPerWarp; ++t) sp->blocks[w][t] = -1;
+        for (int t = 0; t < kMaxGroupsPerWarp; ++t) sp->groups[w][t] = -1;
+    }
+    auto least = [&](const int* cnt, int cap) {
+        int best = -1;
+        for (int w = 0; w < kStreamWarps; ++w)
+            if (cnt[w] < cap && (best < 0 || load[w] < load[best])) best = w;
+        return best;
+    };
+    for (int b = 0; b < fp.n10; ++b) {
+        const int w = least(nb, kMaxBlocksPerWarp);
+        if (w < 0) return false;
+        sp->blocks[w][nb[w]++] = static_cast<signed char>(b);
+        load[w] += 2.4;
+    }
+    for (int g = 0; g < 32; ++g) {
+        const int w = least(ng, kMaxGroupsPerWarp);
+        if (w < 0) return false;
+        sp->groups[w][ng[w]++] = static_cast<signed char>(g);
+        load[w] += 1.0;
+    }
+    return true;
+}
+
 // Appended elements that make `levels` halvings of a node of `n` elements block-regular: whenever the current
 // level holds an odd number m of elements (each covering `w` base elements) the reflect rule pairs the last one
 // with element m-2, i.e. the base range of element m-2 is appended.  tab[e] = source of appended base element n+e.
@@ -395,6 +682,44 @@ extern "C" int afd_haar_fingerprint_accum(const float* x, int64_t B, int64_t N, 
         AFD_CUDA_TRY(cudaGetDevice(&dev));
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const size_t smem = 4ull * fp.buf_floats;
+        const char* impl = getenv("AFD_HAAR_IMPL");       // "fast": the two-CTA kernel without prefetch (A/B, cross-check)
+        HaarStreamPlan sp;
+        if (2 * smem + 2 * 8 * kStreamWarps * kMaxBlocksPerWarp <= static_cast<size_t>(kMaxSmemPerCta) && !(impl && strcmp(impl, "fast") == 0) &&
+            (reinterpret_cast<uintptr_t>(x) & 7) == 0 && (x_row_stride & 1) == 0 && make_stream_plan(fp, &sp)) {
+            long long grid = sms;
+            if (grid > B) grid = B;
+#define AFD_HAAR_STREAM(KK)                                                                                          \
+            case KK: {                                                                                               \
+                static thread_local bool configured[16] = {false};                                                   \
+                if (dev >= 16 || !configured[dev]) {                                                                 \
+                    AFD_CUDA_TRY(cudaFuncSetAttribute(haar_stream_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta)); \
+                    if (dev < 16) configured[dev] = true;                                                            \
+                }                                                                                                    \
+                haar_stream_kernel<KK><<<static_cast<unsigned>(grid), kStreamThreads, 2 * smem + 2 * 8 * kStreamWarps * kMaxBlocksPerWarp, s>>>(                \
+                    x, static_cast<long long>(x_row_stride), static_cast<long long>(B), sums, sp);                    \
+                break;                                                                                               \
+            }
+            switch (level - 10) { AFD_HAAR_STREAM(1) AFD_HAAR_STREAM(2) AFD_HAAR_STREAM(3) AFD_HAAR_STREAM(4) }
+#undef AFD_HAAR_STREAM
+            AFD_CUDA_TRY(cudaGetLastError());
+#if AFD_HAAR_PHASE_TIMING
+            {
+                unsigned long long h[8];
+                cudaDeviceSynchronize();
+                cudaMemcpyFromSymbol(h, g_haar_phase, sizeof(h));
+                const double clips = static_cast<double>(B);
+                fprintf(stderr, "haar stream phases (cycles per clip; issue+C, wait, AB, barrier) warp0: %.0f %.0f %.0f %.0f | warp15: %.0f %.0f %.0f %.0f\n",
+                        h[0] / clips, h[1] / clips, h[2] / clips, h[3] / clips, h[4] / clips, h[5] / clips, h[6] / clips, h[7] / clips);
+                memset(h, 0, sizeof(h));
+                cudaMemcpyToSymbol(g_haar_phase, h, sizeof(h));
+            }
+#endif
+            if (count) {
+                add_count_kernel<<<1, 1, 0, s>>>(reinterpret_cast<long long*>(count), static_cast<long long>(B) * fp.nL);
+                AFD_CUDA_TRY(cudaGetLastError());
+            }
+            return AFD_OK;
+        }
         long long grid = 2LL * sms;
         if (grid > B) grid = B;
 #define AFD_HAAR_FAST(KK)                                                                                            \
