@@ -360,6 +360,7 @@ haar_fast_kernel(const float* __restrict__ x, long long x_row_stride, long long 
 #endif
 #if AFD_HAAR_PHASE_TIMING
 static __device__ unsigned long long g_haar_phase[8];
+static __device__ unsigned long long g_haar_warp[16];
 #define AFD_HAAR_MARK(slot)                                                                          \
     do {                                                                                             \
         if (lane == 0 && (warp == 0 || warp == 15)) {                                                \
@@ -582,6 +583,280 @@ haar_stream_kernel(const float* __restrict__ x, long long x_row_stride, long lon
     if (since_flush) flush();
 }
 
+// ================================================================================================
+// Linear-layout variant (r2): the streaming kernel above still spends a quarter of its warps on issuing cp.async (each
+// LDGSTS occupies its warp for ~90 cycles, and the copies crowd the same LSU queue the workers' LDS / STS go through).
+// A whole clip can be staged by ONE bulk copy (TMA engine, no thread involved, nothing in the LSU queue) -- if it may land
+// contiguously.  The 36-float row padding of the layout above exists only for pass A (a lane owns a 128-byte row; 32 lanes
+// reading the same float4 column of 32 rows is an 8-way bank conflict).  Here the clip stays LINEAR and pass A reads
+// float2 column (u ^ k) of its row in step u, k = row & 15: the 16 lanes of a half warp hit 16 distinct float2 columns.
+// The Haar stages are Walsh-Hadamard butterflies, and a WHT of an XOR-permuted input is the WHT times a Walsh sign:
+//     in'[q] = in[q ^ k]  =>  out'[h] = (-1)^<k, h> out[h]
+// so pass A runs the unchanged butterflies on the permuted registers and writes them back in place: row r now holds
+// output pair hq at float2 column hq ^ k with sign (-1)^<k, hq>.  Pass B (lane = column c, WHT along the 32 rows j of a
+// block) reads row j at float (c ^ 2 (j & 15)), i.e. its input carries the sign (-1)^<j & 15, c >> 1> -- a Walsh function of
+// j -- and a WHT of a Walsh-modulated input is the WHT XOR-permuted: register m holds output m ^ (c >> 1).  Pass B stores
+// register m to row m ^ (c >> 1), plain column c: signs and permutations cancel with no extra arithmetic, and pass C reads a
+// plain [element][node] array.  Odd clips (88,200 B apart: 8-byte aligned) are copied from 8 bytes earlier; all indices are
+// then shifted by sh = 2 floats, which the float2 accesses of pass A and the scalar accesses of passes B / C absorb.
+// All 16 warps work; blocks and node groups are dealt by the same greedy schedule.
+// ================================================================================================
+constexpr int kLinChunks = 4;             // bulk copies (and mbarriers) per clip
+
+struct HaarLinearPlan {
+    HaarFastPlan fast;
+    int ext_block;
+    int buf_floats;                                   // floats per clip buffer (linear clip + shift + appended samples)
+    int chunk_first[kLinChunks + 1];                  // chunk c covers blocks [chunk_first[c], chunk_first[c + 1])
+    signed char blocks[kStreamWarps][kMaxBlocksPerWarp];
+    signed char groups[kStreamWarps][kMaxGroupsPerWarp];
+};
+
+template <int K>
+__global__ void __launch_bounds__(kStreamThreads, 1)
+haar_linear_kernel(const float* __restrict__ x, long long x_row_stride, long long B, double* __restrict__ sums,
+                   const __grid_constant__ HaarLinearPlan sp) {
+    extern __shared__ __align__(128) float smem_h[];
+    constexpr int BLK = 1 << K;
+    const HaarFastPlan& plan = sp.fast;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int n5 = plan.n5, n10 = plan.n10, N = plan.N;
+    float acc[kMaxGroupsPerWarp][BLK];
+#pragma unroll
+    for (int q = 0; q < kMaxGroupsPerWarp; ++q)
+#pragma unroll
+        for (int c = 0; c < BLK; ++c) acc[q][c] = 0.f;
+
+    auto flush = [&]() {
+#pragma unroll
+        for (int q = 0; q < kMaxGroupsPerWarp; ++q) {
+            const int g = sp.groups[warp][q];
+            if (g < 0) continue;
+            const unsigned o = static_cast<unsigned>(32 * g + lane);       // level-10 node (LSB-first path)
+#pragma unroll
+            for (int c = 0; c < BLK; ++c) {
+                const unsigned node = o + (static_cast<unsigned>(c) << 10);
+                const unsigned nat = bitrev(node, plan.L);
+                unsigned p = nat;
+                for (int sft = 1; sft < plan.L; sft <<= 1) p ^= p >> sft;
+                atomicAdd(sums + p, static_cast<double>(acc[q][c]) * static_cast<double>(plan.final_scale));
+                acc[q][c] = 0.f;
+            }
+        }
+    };
+
+    float* const buf0 = smem_h;
+    float* const buf1 = smem_h + sp.buf_floats;
+    const uint32_t mbar0 = static_cast<uint32_t>(__cvta_generic_to_shared(smem_h + 2 * sp.buf_floats));
+    auto mbar = [&](int bufi, int c) { return mbar0 + 8u * static_cast<uint32_t>(bufi * kLinChunks + c); };
+    if (tid < 2 * kLinChunks) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar0 + 8u * tid), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    auto shift_of = [&](const float* xg) { return (static_cast<unsigned>(reinterpret_cast<uintptr_t>(xg)) & 15u) ? 2 : 0; };
+
+    // Stage a clip (warp 0): chunk c = one bulk copy of the floats [4 f0, 4 f1) of the 16-byte aligned array that starts
+    // sh floats before the clip; what does not fill a 16-byte unit at the clip's end is moved by lanes (never reads past x).
+    auto load_clip = [&](float* buf, int bufi, const float* xg) {
+        const int sh = shift_of(xg);
+        const float* src = xg - sh;                                        // 16-byte aligned
+        const int total4 = (N + sh) >> 2;                                  // whole float4 units inside the clip
+        for (int s = 4 * total4 - sh + lane; s < N; s += 32) buf[sh + s] = __ldg(xg + s);     // <= 3 tail samples
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic accesses of the free buffer before the async writes
+        __syncwarp();
+        if (lane < kLinChunks) {
+            const int c = lane;
+            int f0 = (1024 * sp.chunk_first[c]) >> 2, f1 = (1024 * sp.chunk_first[c + 1]) >> 2;
+            if (c == kLinChunks - 1 || f1 > total4) f1 = total4;
+            if (f0 > total4) f0 = total4;
+            // shifted clips: float index = sample + 2, so chunk boundaries (sample multiples of 1024) sit 2 floats into a
+            // unit; a unit that straddles two chunks is counted with the LATER chunk's barrier only through f0's rounding:
+            // every unit belongs to exactly one copy because consecutive chunks share f1 == next f0.
+            const uint32_t bytes = static_cast<uint32_t>(f1 - f0) * 16u;
+            const uint32_t bar = mbar(bufi, c);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            if (bytes) {
+                const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(buf + 4 * f0));
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "l"(src + 4 * f0), "r"(bytes), "r"(bar) : "memory");
+            }
+        }
+    };
+    auto wait_chunk = [&](int bufi, int c, uint32_t parity) {
+        const uint32_t a = mbar(bufi, c);
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        }
+    };
+    // a block's samples [1024 b - ?, ...): with the shift its first two floats belong to the previous chunk's last unit, so a
+    // block waits for its own chunk and (shifted clips, first block of a chunk) the previous one
+    auto wait_block = [&](int bufi, int b, int sh, uint32_t parity) {
+        int c = 0;
+#pragma unroll
+        for (int t = 1; t < kLinChunks; ++t) c += b >= sp.chunk_first[t] ? 1 : 0;
+        wait_chunk(bufi, c, parity);
+        if (sh != 0 && c + 1 < kLinChunks && b + 1 == sp.chunk_first[c + 1]) wait_chunk(bufi, c + 1, parity);   // its last 2 samples
+        if (b == sp.ext_block) wait_chunk(bufi, kLinChunks - 1, parity);                                          // tail samples
+    };
+
+    // passes A and B of block b, in place, by one warp
+    auto pass_ab = [&](float* buf, int b, int sh) {
+        float* const lin = buf + sh;                        // sample s of the clip at lin[s]
+        if (b == sp.ext_block) {
+            // Appended samples (copies of samples of this block, host-checked), then the appended level-5 elements: instead
+            // of copying a source row's pass-A OUTPUT (which would need the target row's sign / column convention), the
+            // source row's raw samples are duplicated and the otherwise idle lanes of this block transform the copies.
+            if (lane < plan.extA) lin[N + lane] = lin[plan.tabA[lane]];
+            __syncwarp();
+            for (int e = 0; e < plan.extB; ++e) lin[32 * (n5 + e) + lane] = lin[32 * plan.tabB[e] + lane];
+            __syncwarp();
+        }
+        const int r = 32 * b + lane;                        // pass A: lane = row, float2 column u ^ k in step u
+        const int k = lane & 15;
+        if (r < n5 + plan.extB) {
+            float v[32];
+            float2* rowp = reinterpret_cast<float2*>(lin + 32 * r);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const float2 q2 = rowp[u ^ k];
+                v[2 * u] = q2.x; v[2 * u + 1] = q2.y;
+            }
+            haar_stage<1>(v); haar_stage<2>(v); haar_stage<4>(v); haar_stage<8>(v); haar_stage<16>(v);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) rowp[u ^ k] = make_float2(v[2 * u], v[2 * u + 1]);
+        }
+        __syncwarp();
+        {                                                   // pass B: lane = level-5 node c, the block's 32 elements (rows)
+            float v[32];
+            float* base = lin + 1024 * b;
+            const int hl = lane >> 1;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = base[32 * j + (lane ^ ((j & 15) << 1))];
+            haar_stage<1>(v); haar_stage<2>(v); haar_stage<4>(v); haar_stage<8>(v); haar_stage<16>(v);
+            __syncwarp();                                   // every lane has read the tile before anybody overwrites it
+#pragma unroll
+            for (int m = 0; m < 32; ++m) base[32 * ((m & 16) | ((m ^ hl) & 15)) + lane] = v[m];
+        }
+    };
+
+    int cur = 0;
+    int since_flush = 0;
+    long long it = 0;
+    if (blockIdx.x < B) {
+        const float* xg = x + blockIdx.x * x_row_stride;
+        if (warp == 0) load_clip(buf0, 0, xg);
+        const int sh = shift_of(xg);
+#pragma unroll
+        for (int t = 0; t < kMaxBlocksPerWarp; ++t)
+            if (sp.blocks[warp][t] >= 0) { wait_block(0, sp.blocks[warp][t], sh, 0); pass_ab(buf0, sp.blocks[warp][t], sh); }
+    }
+    __syncthreads();
+#if AFD_HAAR_PHASE_TIMING
+    long long t0_ = clock64();
+#endif
+    for (long long clip = blockIdx.x; clip < B; clip += gridDim.x, cur ^= 1, ++it) {
+        float* const buf = cur ? buf1 : buf0;
+        float* const nbuf = cur ? buf0 : buf1;
+        const bool more = clip + gridDim.x < B;
+        const float* xn = x + (clip + gridDim.x) * x_row_stride;
+#if AFD_HAAR_PHASE_TIMING
+        const long long it0_ = clock64();
+#endif
+        if (more && warp == 0) load_clip(nbuf, cur ^ 1, xn);              // the other buffer's pass C ended before the last barrier
+        // ---- pass C of this clip: levels 11-L, lane = level-10 node of one of the warp's groups; |c| accumulates in registers
+        const float* lin = buf + shift_of(x + clip * x_row_stride);
+#pragma unroll
+        for (int q = 0; q < kMaxGroupsPerWarp; ++q) {
+            const int g = sp.groups[warp][q];
+            if (g < 0) continue;
+            const float* base = lin + 32 * g + lane;                      // element i of node o = 32 g + lane at base[1024 i]
+            for (int b = 0; b < plan.nL; ++b) {
+                float v[16];
+                const bool redirect = (b + 1) * BLK > n10;
+#pragma unroll
+                for (int j = 0; j < BLK; ++j) {
+                    int i = b * BLK + j;
+                    if (redirect && i >= n10) i = plan.tabC[i - n10];
+                    v[j] = base[1024 * i];
+                }
+                if (K >= 1) haar_stage16<1>(v);
+                if (K >= 2) haar_stage16<2>(v);
+                if (K >= 3) haar_stage16<4>(v);
+                if (K >= 4) haar_stage16<8>(v);
+#pragma unroll
+                for (int c = 0; c < BLK; ++c) acc[q][c] += fabsf(v[c]);
+            }
+        }
+        if (++since_flush == kFlushEvery) { flush(); since_flush = 0; }
+        AFD_HAAR_MARK(0);
+        // ---- passes A and B of the next clip's blocks, each as soon as its chunk has landed
+        if (more) {
+            const uint32_t parity = static_cast<uint32_t>(((it + 1) >> 1) & 1);
+            const int nsh = shift_of(xn);
+#pragma unroll
+            for (int t = 0; t < kMaxBlocksPerWarp; ++t)
+                if (sp.blocks[warp][t] >= 0) {
+                    wait_block(cur ^ 1, sp.blocks[warp][t], nsh, parity);
+                    AFD_HAAR_MARK(1);
+                    pass_ab(nbuf, sp.blocks[warp][t], nsh);
+                    AFD_HAAR_MARK(2);
+                }
+        }
+#if AFD_HAAR_PHASE_TIMING
+        if (lane == 0) atomicAdd(&g_haar_warp[warp], static_cast<unsigned long long>(clock64() - it0_));
+#endif
+        __syncthreads();
+        AFD_HAAR_MARK(3);
+    }
+    if (since_flush) flush();
+}
+
+static bool make_stream_schedule(int n10, int workers, signed char (*blocks)[kMaxBlocksPerWarp], signed char (*groups)[kMaxGroupsPerWarp]) {
+    if (n10 > workers * kMaxBlocksPerWarp || 32 > workers * kMaxGroupsPerWarp) return false;
+    double load[kStreamWarps] = {0};
+    int nb[kStreamWarps] = {0}, ng[kStreamWarps] = {0};
+    for (int w = 0; w < kStreamWarps; ++w) {
+        for (int t = 0; t < kMaxBlocksPerWarp; ++t) blocks[w][t] = -1;
+        for (int t = 0; t < kMaxGroupsPerWarp; ++t) groups[w][t] = -1;
+        if (w >= workers) { nb[w] = kMaxBlocksPerWarp; ng[w] = kMaxGroupsPerWarp; }
+    }
+    auto least = [&](const int* cnt, int cap) {
+        int best = -1;
+        for (int w = 0; w < kStreamWarps; ++w)
+            if (cnt[w] < cap && (best < 0 || load[w] < load[best])) best = w;
+        return best;
+    };
+    for (int b = 0; b < n10; ++b) {
+        const int w = least(nb, kMaxBlocksPerWarp);
+        if (w < 0) return false;
+        blocks[w][nb[w]++] = static_cast<signed char>(b);
+        load[w] += 2.4;
+    }
+    for (int g = 0; g < 32; ++g) {
+        const int w = least(ng, kMaxGroupsPerWarp);
+        if (w < 0) return false;
+        groups[w][ng[w]++] = static_cast<signed char>(g);
+        load[w] += 1.0;
+    }
+    return true;
+}
+
+static bool make_linear_plan(const HaarFastPlan& fp, HaarLinearPlan* lp) {
+    lp->fast = fp;
+    lp->ext_block = (fp.n5 - 1) >> 5;
+    if (fp.extA > 32 || ((fp.N + fp.extA - 1) >> 10) != lp->ext_block || ((fp.N - 1) >> 10) != lp->ext_block) return false;
+    for (int e = 0; e < fp.extB; ++e)
+        if ((fp.tabB[e] >> 5) != lp->ext_block || ((fp.n5 + e) >> 5) != lp->ext_block) return false;
+    for (int e = 0; e < fp.extA; ++e)
+        if ((fp.tabA[e] >> 10) != lp->ext_block) return false;
+    if (lp->ext_block != fp.n10 - 1) return false;                        // the tail lives in the last block (and last chunk)
+    lp->buf_floats = (1024 * fp.n10 + 2 + 31) / 32 * 32;                  // linear clip incl. appended rows, + shift; 128-byte multiple
+    for (int c = 0; c <= kLinChunks; ++c) lp->chunk_first[c] = static_cast<int>(static_cast<long long>(fp.n10) * c / kLinChunks);
+    return make_stream_schedule(fp.n10, kStreamWarps, lp->blocks, lp->groups);
+}
+
 // Greedy schedule: blocks (cost 2.4) then node groups (cost 1) to the least loaded warp.
 static bool make_stream_plan(const HaarFastPlan& fp, HaarStreamPlan* sp) {
     sp->fast = fp;
@@ -682,7 +957,52 @@ extern "C" int afd_haar_fingerprint_accum(const float* x, int64_t B, int64_t N, 
         AFD_CUDA_TRY(cudaGetDevice(&dev));
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const size_t smem = 4ull * fp.buf_floats;
-        const char* impl = getenv("AFD_HAAR_IMPL");       // "fast": the two-CTA kernel without prefetch (A/B, cross-check)
+        const char* impl = getenv("AFD_HAAR_IMPL");       // "stream" / "fast": the earlier kernels (A/B, cross-checks)
+        HaarLinearPlan lp;
+        if (!impl && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_row_stride & 1) == 0 && make_linear_plan(fp, &lp) &&
+            2 * 4ull * lp.buf_floats + 8 * 2 * kLinChunks <= static_cast<size_t>(kMaxSmemPerCta)) {
+            long long grid = sms;
+            if (grid > B) grid = B;
+            const size_t lsmem = 2 * 4ull * lp.buf_floats + 8 * 2 * kLinChunks;
+#define AFD_HAAR_LINEAR(KK)                                                                                          \
+            case KK: {                                                                                               \
+                static thread_local bool configured[16] = {false};                                                   \
+                if (dev >= 16 || !configured[dev]) {                                                                 \
+                    AFD_CUDA_TRY(cudaFuncSetAttribute(haar_linear_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta)); \
+                    if (dev < 16) configured[dev] = true;                                                            \
+                }                                                                                                    \
+                haar_linear_kernel<KK><<<static_cast<unsigned>(grid), kStreamThreads, lsmem, s>>>(                   \
+                    x, static_cast<long long>(x_row_stride), static_cast<long long>(B), sums, lp);                    \
+                break;                                                                                               \
+            }
+            switch (level - 10) { AFD_HAAR_LINEAR(1) AFD_HAAR_LINEAR(2) AFD_HAAR_LINEAR(3) AFD_HAAR_LINEAR(4) }
+#undef AFD_HAAR_LINEAR
+            AFD_CUDA_TRY(cudaGetLastError());
+#if AFD_HAAR_PHASE_TIMING
+            {
+                unsigned long long h[8];
+                cudaDeviceSynchronize();
+                cudaMemcpyFromSymbol(h, g_haar_phase, sizeof(h));
+                const double clips = static_cast<double>(B);
+                unsigned long long hw[16];
+                cudaMemcpyFromSymbol(hw, g_haar_warp, sizeof(hw));
+                fprintf(stderr, "haar linear: cycles from iteration start to barrier arrival per warp:");
+                for (int w = 0; w < 16; ++w) fprintf(stderr, " %.0f", hw[w] / static_cast<double>(B));
+                fprintf(stderr, "\n");
+                memset(hw, 0, sizeof(hw));
+                cudaMemcpyToSymbol(g_haar_warp, hw, sizeof(hw));
+                fprintf(stderr, "haar linear phases (cycles per clip; C, wait, AB, barrier) warp0: %.0f %.0f %.0f %.0f | warp15: %.0f %.0f %.0f %.0f\n",
+                        h[0] / clips, h[1] / clips, h[2] / clips, h[3] / clips, h[4] / clips, h[5] / clips, h[6] / clips, h[7] / clips);
+                memset(h, 0, sizeof(h));
+                cudaMemcpyToSymbol(g_haar_phase, h, sizeof(h));
+            }
+#endif
+            if (count) {
+                add_count_kernel<<<1, 1, 0, s>>>(reinterpret_cast<long long*>(count), static_cast<long long>(B) * fp.nL);
+                AFD_CUDA_TRY(cudaGetLastError());
+            }
+            return AFD_OK;
+        }
         HaarStreamPlan sp;
         if (2 * smem + 2 * 8 * kStreamWarps * kMaxBlocksPerWarp <= static_cast<size_t>(kMaxSmemPerCta) && !(impl && strcmp(impl, "fast") == 0) &&
             (reinterpret_cast<uintptr_t>(x) & 7) == 0 && (x_row_stride & 1) == 0 && make_stream_plan(fp, &sp)) {
