@@ -602,18 +602,29 @@ haar_stream_kernel(const float* __restrict__ x, long long x_row_stride, long lon
 // All 16 warps work; blocks and node groups are dealt by the same greedy schedule.
 // ================================================================================================
 constexpr int kLinChunks = 4;             // bulk copies (and mbarriers) per clip
+#ifndef AFD_HAAR_LIN_THREADS
+#define AFD_HAAR_LIN_THREADS 512
+#endif
+constexpr int kLinThreads = AFD_HAAR_LIN_THREADS;
+constexpr int kLinWarps = kLinThreads / 32;
+constexpr int kLinMaxWarps = 32;
+constexpr int kLinGroups = (32 + kLinWarps - 1) / kLinWarps + (kLinWarps < 22 ? 1 : 0);   // node groups a warp may own (acc registers)
 
 struct HaarLinearPlan {
     HaarFastPlan fast;
     int ext_block;
     int buf_floats;                                   // floats per clip buffer (linear clip + shift + appended samples)
     int chunk_first[kLinChunks + 1];                  // chunk c covers blocks [chunk_first[c], chunk_first[c + 1])
-    signed char blocks[kStreamWarps][kMaxBlocksPerWarp];
-    signed char groups[kStreamWarps][kMaxGroupsPerWarp];
+    signed char blocks[kLinMaxWarps][kMaxBlocksPerWarp];
+    signed char groups[kLinMaxWarps][kMaxGroupsPerWarp];
 };
 
-template <int K>
-__global__ void __launch_bounds__(kStreamThreads, 1)
+// HEAD: the reference's shape (22050-sample clips, level 14: 22 level-10 elements per node, appended elements 22, 23 = copies of
+// 18, 19 and 24 .. 31 = copies of 8 .. 15): pass C's element offsets are compile-time immediates.
+__host__ __device__ constexpr int head_elem(int i) { return i < 22 ? i : (i < 24 ? i - 4 : i - 16); }
+
+template <int K, bool HEAD>
+__global__ void __launch_bounds__(kLinThreads, 1)
 haar_linear_kernel(const float* __restrict__ x, long long x_row_stride, long long B, double* __restrict__ sums,
                    const __grid_constant__ HaarLinearPlan sp) {
     extern __shared__ __align__(128) float smem_h[];
@@ -622,15 +633,17 @@ haar_linear_kernel(const float* __restrict__ x, long long x_row_stride, long lon
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int n5 = plan.n5, n10 = plan.n10, N = plan.N;
-    float acc[kMaxGroupsPerWarp][BLK];
+    float acc[kLinGroups][BLK];
 #pragma unroll
-    for (int q = 0; q < kMaxGroupsPerWarp; ++q)
+    for (int q = 0; q < kLinGroups; ++q)
 #pragma unroll
         for (int c = 0; c < BLK; ++c) acc[q][c] = 0.f;
 
+    // (Measured alternative: a private [grid][2^L] slab with plain fp64 read-modify-write + a reduce kernel instead of the
+    // 148 x 16384 atomics per flush is 9 % SLOWER -- the RED.ADD.F64 are fire-and-forget, the slab's loads are not.)
     auto flush = [&]() {
 #pragma unroll
-        for (int q = 0; q < kMaxGroupsPerWarp; ++q) {
+        for (int q = 0; q < kLinGroups; ++q) {
             const int g = sp.groups[warp][q];
             if (g < 0) continue;
             const unsigned o = static_cast<unsigned>(32 * g + lane);       // level-10 node (LSB-first path)
@@ -768,25 +781,37 @@ haar_linear_kernel(const float* __restrict__ x, long long x_row_stride, long lon
         // ---- pass C of this clip: levels 11-L, lane = level-10 node of one of the warp's groups; |c| accumulates in registers
         const float* lin = buf + shift_of(x + clip * x_row_stride);
 #pragma unroll
-        for (int q = 0; q < kMaxGroupsPerWarp; ++q) {
+        for (int q = 0; q < kLinGroups; ++q) {
             const int g = sp.groups[warp][q];
             if (g < 0) continue;
             const float* base = lin + 32 * g + lane;                      // element i of node o = 32 g + lane at base[1024 i]
-            for (int b = 0; b < plan.nL; ++b) {
-                float v[16];
-                const bool redirect = (b + 1) * BLK > n10;
+            if constexpr (HEAD) {
 #pragma unroll
-                for (int j = 0; j < BLK; ++j) {
-                    int i = b * BLK + j;
-                    if (redirect && i >= n10) i = plan.tabC[i - n10];
-                    v[j] = base[1024 * i];
+                for (int b = 0; b < 2; ++b) {
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = base[1024 * head_elem(16 * b + j)];
+                    haar_stage16<1>(v); haar_stage16<2>(v); haar_stage16<4>(v); haar_stage16<8>(v);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) acc[q][c] += fabsf(v[c]);
                 }
-                if (K >= 1) haar_stage16<1>(v);
-                if (K >= 2) haar_stage16<2>(v);
-                if (K >= 3) haar_stage16<4>(v);
-                if (K >= 4) haar_stage16<8>(v);
+            } else {
+                for (int b = 0; b < plan.nL; ++b) {
+                    float v[16];
+                    const bool redirect = (b + 1) * BLK > n10;
 #pragma unroll
-                for (int c = 0; c < BLK; ++c) acc[q][c] += fabsf(v[c]);
+                    for (int j = 0; j < BLK; ++j) {
+                        int i = b * BLK + j;
+                        if (redirect && i >= n10) i = plan.tabC[i - n10];
+                        v[j] = base[1024 * i];
+                    }
+                    if (K >= 1) haar_stage16<1>(v);
+                    if (K >= 2) haar_stage16<2>(v);
+                    if (K >= 3) haar_stage16<4>(v);
+                    if (K >= 4) haar_stage16<8>(v);
+#pragma unroll
+                    for (int c = 0; c < BLK; ++c) acc[q][c] += fabsf(v[c]);
+                }
             }
         }
         if (++since_flush == kFlushEvery) { flush(); since_flush = 0; }
@@ -813,18 +838,18 @@ haar_linear_kernel(const float* __restrict__ x, long long x_row_stride, long lon
     if (since_flush) flush();
 }
 
-static bool make_stream_schedule(int n10, int workers, signed char (*blocks)[kMaxBlocksPerWarp], signed char (*groups)[kMaxGroupsPerWarp]) {
-    if (n10 > workers * kMaxBlocksPerWarp || 32 > workers * kMaxGroupsPerWarp) return false;
-    double load[kStreamWarps] = {0};
-    int nb[kStreamWarps] = {0}, ng[kStreamWarps] = {0};
-    for (int w = 0; w < kStreamWarps; ++w) {
+static bool make_stream_schedule(int n10, int workers, int max_groups, signed char (*blocks)[kMaxBlocksPerWarp], signed char (*groups)[kMaxGroupsPerWarp]) {
+    if (n10 > workers * kMaxBlocksPerWarp || 32 > workers * max_groups) return false;
+    double load[kLinMaxWarps] = {0};
+    int nb[kLinMaxWarps] = {0}, ng[kLinMaxWarps] = {0};
+    for (int w = 0; w < kLinMaxWarps; ++w) {
         for (int t = 0; t < kMaxBlocksPerWarp; ++t) blocks[w][t] = -1;
         for (int t = 0; t < kMaxGroupsPerWarp; ++t) groups[w][t] = -1;
-        if (w >= workers) { nb[w] = kMaxBlocksPerWarp; ng[w] = kMaxGroupsPerWarp; }
+        if (w >= workers) { nb[w] = kMaxBlocksPerWarp; ng[w] = max_groups; }
     }
     auto least = [&](const int* cnt, int cap) {
         int best = -1;
-        for (int w = 0; w < kStreamWarps; ++w)
+        for (int w = 0; w < kLinMaxWarps; ++w)
             if (cnt[w] < cap && (best < 0 || load[w] < load[best])) best = w;
         return best;
     };
@@ -835,7 +860,7 @@ static bool make_stream_schedule(int n10, int workers, signed char (*blocks)[kMa
         load[w] += 2.4;
     }
     for (int g = 0; g < 32; ++g) {
-        const int w = least(ng, kMaxGroupsPerWarp);
+        const int w = least(ng, max_groups);
         if (w < 0) return false;
         groups[w][ng[w]++] = static_cast<signed char>(g);
         load[w] += 1.0;
@@ -854,7 +879,7 @@ static bool make_linear_plan(const HaarFastPlan& fp, HaarLinearPlan* lp) {
     if (lp->ext_block != fp.n10 - 1) return false;                        // the tail lives in the last block (and last chunk)
     lp->buf_floats = (1024 * fp.n10 + 2 + 31) / 32 * 32;                  // linear clip incl. appended rows, + shift; 128-byte multiple
     for (int c = 0; c <= kLinChunks; ++c) lp->chunk_first[c] = static_cast<int>(static_cast<long long>(fp.n10) * c / kLinChunks);
-    return make_stream_schedule(fp.n10, kStreamWarps, lp->blocks, lp->groups);
+    return make_stream_schedule(fp.n10, kLinWarps, kLinGroups < kMaxGroupsPerWarp ? kLinGroups : kMaxGroupsPerWarp, lp->blocks, lp->groups);
 }
 
 // Greedy schedule: blocks (cost 2.4) then node groups (cost 1) to the least loaded warp.
@@ -964,18 +989,24 @@ extern "C" int afd_haar_fingerprint_accum(const float* x, int64_t B, int64_t N, 
             long long grid = sms;
             if (grid > B) grid = B;
             const size_t lsmem = 2 * 4ull * lp.buf_floats + 8 * 2 * kLinChunks;
-#define AFD_HAAR_LINEAR(KK)                                                                                          \
-            case KK: {                                                                                               \
+#define AFD_HAAR_LINEAR(KK, HH)                                                                                      \
+            {                                                                                                        \
                 static thread_local bool configured[16] = {false};                                                   \
                 if (dev >= 16 || !configured[dev]) {                                                                 \
-                    AFD_CUDA_TRY(cudaFuncSetAttribute(haar_linear_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta)); \
+                    AFD_CUDA_TRY(cudaFuncSetAttribute(haar_linear_kernel<KK, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta)); \
                     if (dev < 16) configured[dev] = true;                                                            \
                 }                                                                                                    \
-                haar_linear_kernel<KK><<<static_cast<unsigned>(grid), kStreamThreads, lsmem, s>>>(                   \
+                haar_linear_kernel<KK, HH><<<static_cast<unsigned>(grid), kLinThreads, lsmem, s>>>(               \
                     x, static_cast<long long>(x_row_stride), static_cast<long long>(B), sums, lp);                    \
-                break;                                                                                               \
             }
-            switch (level - 10) { AFD_HAAR_LINEAR(1) AFD_HAAR_LINEAR(2) AFD_HAAR_LINEAR(3) AFD_HAAR_LINEAR(4) }
+            bool head = level == 14 && fp.n10 == 22 && fp.nL == 2 && fp.extC == 10;
+            for (int e = 0; head && e < 10; ++e) head = fp.tabC[e] == head_elem(22 + e);
+            switch (level - 10) {
+                case 1: AFD_HAAR_LINEAR(1, false) break;
+                case 2: AFD_HAAR_LINEAR(2, false) break;
+                case 3: AFD_HAAR_LINEAR(3, false) break;
+                case 4: if (head) AFD_HAAR_LINEAR(4, true) else AFD_HAAR_LINEAR(4, false) break;
+            }
 #undef AFD_HAAR_LINEAR
             AFD_CUDA_TRY(cudaGetLastError());
 #if AFD_HAAR_PHASE_TIMING
