@@ -46,9 +46,16 @@ def test_golden_vectors(golden_dir, golden_frames, cuda_device):
 def test_matches_torch_stft(n_fft, hop, N, B, cuda_device):
     rng = np.random.default_rng(n_fft + hop)
     x = (rng.standard_normal((B, 1, N)) * 0.1).astype(np.float32)
-    want = ptwt_like.stft_power_explicit(torch.from_numpy(x).double(), n_fft, hop).numpy()
+    want = ptwt_like.stft_power_dft64(x[:, 0], n_fft, hop)[:, None]              # fp64 truth, numpy only
+    # torch.stft on the CPU (the reference's code path in fp64) must agree with it.  On the GPU box this call has
+    # returned non-finite values when it was the first CPU FFT after cuDNN / pinned-memory work in the same process (seen
+    # only inside the full suite, never alone); the product is compared with the numpy truth either way.
+    ref = ptwt_like.stft_power_explicit(torch.from_numpy(x).double(), n_fft, hop).numpy()
+    if np.isfinite(ref).all():
+        assert ref.shape == want.shape and _rel(ref, want) < 1e-9
     got = afd.STFTLayer(n_fft=n_fft, hop_length=hop)(torch.from_numpy(x).to(cuda_device))[0].cpu().numpy()
     assert got.shape == want.shape
+    assert np.isfinite(got).all(), np.argwhere(~np.isfinite(got))[:12].tolist()
     assert _rel(got, want) < TOL
 
 
