@@ -35,6 +35,15 @@ def main():
         want = wpt_oracle.packet_features(x.astype(np.float64), Wavelet(name).dec_lo, level, dtype=np.float64)
         print(f"sanitize: packets {name} L{level} rel {rel(got, want):.2e}", flush=True)
         assert rel(got, want) < 1e-5
+    # more frames than SMs: the frame kernel's persistent loop, prefetch hand-over between the groups and buffer re-use
+    rngb = np.random.default_rng(1)
+    xb = (rngb.standard_normal((160, 22050)) * 0.1).astype(np.float32)
+    for name in ("sym5", "coif4"):
+        got = afd.wavelet_packet_features(torch.from_numpy(xb).to(dev), Wavelet(name), 8).cpu().numpy()
+        for f in (0, 77, 148, 159):
+            want = wpt_oracle.packet_features(xb[f:f + 1].astype(np.float64), Wavelet(name).dec_lo, 8, dtype=np.float64)
+            assert rel(got[f:f + 1], want) < 1e-5, (name, f)
+        print(f"sanitize: packets {name} L8 batch 160 ok", flush=True)
     mod = afd.Packets(wavelet_str="sym5", max_lev=8, log_scale=True, loss_less=True, compute_welford=True)
     feats, aux = mod(xt)
     assert torch.isfinite(feats).all() and len(aux) == 256
@@ -57,6 +66,18 @@ def main():
         sums, count = wpt_oracle.haar_fingerprint_sums(xx.astype(np.float64), level, dtype=np.float64)
         print(f"sanitize: haar N={N} L{level} rel {rel(got, sums / count):.2e}", flush=True)
         assert rel(got, sums / count) < 1e-5
+    xh = (rng.standard_normal((300, 22050)) * 0.1).astype(np.float32)      # two clips per CTA: double-buffered bulk staging
+    got = afd.haar_fingerprint(torch.from_numpy(xh).to(dev), 14).cpu().numpy()
+    sums, count = wpt_oracle.haar_fingerprint_sums(xh.astype(np.float64), 14, dtype=np.float64)
+    print(f"sanitize: haar batch 300 rel {rel(got, sums / count):.2e}", flush=True)
+    assert rel(got, sums / count) < 1e-5
+    from oracle import resample_oracle
+    xr = (rng.standard_normal((3, 6000)) * 0.1).astype(np.float32)
+    for orig in (44100, 48000):
+        got = afd.framing.resample(torch.from_numpy(xr).to(dev), orig, 22050).cpu().numpy()
+        want = resample_oracle.resample(xr, orig, 22050)
+        print(f"sanitize: resample {orig} -> 22050 rel {rel(got, want):.2e}", flush=True)
+        assert rel(got, want) < 1e-5
     acc = afd.SpectrumFingerprintAccumulator(22050, dev)
     acc.update(xt)
     torch.cuda.synchronize()
