@@ -495,10 +495,15 @@ class Bench:
             acc = afd.FingerprintAccumulator(level, self.dev)
             job(acc)
             acc.all_reduce()
-        self.barrier()
         acc = afd.FingerprintAccumulator(level, self.dev)
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        align = torch.zeros(1, device=self.dev)
         with ClockSampler(self.dev) as clk:
+            self.barrier()
+            # The ranks leave the host-side barrier milliseconds apart (python, NVML), which a 4 ms job would count as
+            # all-reduce time on the early ranks: a one-element all-reduce lines the STREAMS up, e0 follows it on the device.
+            if self.world > 1:
+                self.dist.all_reduce(align)
             e0.record()
             job(acc)
             e1.record()
