@@ -236,7 +236,10 @@ __device__ __forceinline__ void lattice2(float (&w)[WLEN], const Coefs<F>& cf, f
 #ifndef AFD_WPT_FFMA2
 #define AFD_WPT_FFMA2 1
 #endif
-constexpr int kPackedMaxF = 16;
+#ifndef AFD_WPT_PACKED_MAXF
+#define AFD_WPT_PACKED_MAXF 16
+#endif
+constexpr int kPackedMaxF = AFD_WPT_PACKED_MAXF;
 // Left reflect padding without stores (r1d): the only reader of a node's left padding is the consumer chunk 0 of the
 // next level (when every item size R >= F/2), and for that chunk the reflection x~[-i] = x[i] is a COMPILE-TIME
 // permutation of its own register window (w[j] = w[2F-4-j], j < F-2).  So the producers skip the left mirror stores
