@@ -294,6 +294,12 @@ struct CopyPass {
 #ifndef AFD_WPT_REFL_INTERIOR
 #define AFD_WPT_REFL_INTERIOR 1
 #endif
+#ifndef AFD_WPT_STRIDE_CONGRUENCE
+#define AFD_WPT_STRIDE_CONGRUENCE 1
+#endif
+#ifndef AFD_WPT_PAIRED_STORE
+#define AFD_WPT_PAIRED_STORE 1      // r2: sym5 -3.6 % time, coif4 -1.6 % (same-box A/B, bit-identical)
+#endif
 #ifndef AFD_WPT_KO_MIRRORS
 #define AFD_WPT_KO_MIRRORS 0      // knock-out timing: 1 skips the mirror (padding) stores of the edge items -- wrong results
 #endif
@@ -734,12 +740,21 @@ __device__ __forceinline__ void last_level(const float* __restrict__ in, const P
             }
         }
         if (!extended || ep.store) {
+#if AFD_WPT_PAIRED_STORE
+            // the two children of a parent sit in adjacent columns 2q, 2q + 1 (in either order): one 64-bit streaming store per row
+            // writes whole sectors and halves the store instructions (48 -> 24 per item); the order is resolved by two selects
+            float2* o2 = reinterpret_cast<float2*>(out_b + static_cast<long long>(k0) * P + 2 * static_cast<int>(q));
+#pragma unroll
+            for (int r = 0; r < RL; ++r)
+                if (r < nv) __stcs(o2 + r * (P / 2), make_float2(swap ? hi[r] : lo[r], swap ? lo[r] : hi[r]));
+#else
 #pragma unroll
             for (int r = 0; r < RL; ++r)
                 if (r < nv) {
                     __stcs(o_lo + r * P, lo[r]);
                     __stcs(o_hi + r * P, hi[r]);
                 }
+#endif
         }
     }
     if (extended && ep.node_stats && !ep.stats_simple) flush_node_stats(ep, P, ts);
@@ -1373,7 +1388,17 @@ static int make_frame_plan(int64_t N, int F, int L, int R0, const Tuning& tu, do
         const int padr = padl + (n[l] & 1);
         const int tail_l = padr > r_prod - 1 ? padr : r_prod - 1;
         int s = round_up(n[l] + (padl > tail_l ? padl : tail_l), 4);
-        if (l >= 2 && ((s >> 2) & 1) == 0) s += 4;            // lanes walk across nodes in the last level: odd 16-byte stride
+        if (l == L - 1) {
+            if (l >= 2 && ((s >> 2) & 1) == 0) s += 4;        // lanes walk across nodes in the last level: odd 16-byte stride
+        } else if (AFD_WPT_STRIDE_CONGRUENCE && l >= 2) {
+            // The consumer (level l + 1) walks its lanes along a node, 2R floats apart (conflict-free for R/2 odd), and jumps
+            // to the next node after C items: with stride == C * 2R (mod 32 floats) the jump continues the same progression.
+            const int parents_c = 1 << (l - 1);                                          // per group, as consumer parents
+            const int rc = level_cost(parents_c, n[l + 1], tu.RB, tu.halo) < level_cost(parents_c, n[l + 1], tu.RA, tu.halo) ? tu.RB : tu.RA;
+            const int cc = (n[l + 1] + rc - 1) / rc;
+            const int want = (cc * 2 * rc) & 31;
+            while ((s & 31) != want) s += 4;
+        }
         stride[l] = s;
     }
     // Each group keeps its half tree in its own half of a region: the groups run out of phase, so one group may write

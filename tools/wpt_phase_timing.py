@@ -17,7 +17,8 @@ N, B = 22050, 4096
 
 def main():
     lib = ctypes.CDLL(os.path.abspath(sys.argv[1]))
-    names = sys.argv[2:] or ["sym5", "coif4"]
+    raw = "--raw" in sys.argv            # log_scale = 0: the epilogue without the log
+    names = [a for a in sys.argv[2:] if not a.startswith("--")] or ["sym5", "coif4"]
     x = torch.randn(B, N, device="cuda") * 0.1
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     for name in names:
@@ -29,7 +30,7 @@ def main():
         out = torch.empty(B, 1, T.value, 256, device="cuda")
         for _ in range(3):
             rc = lib.afd_wpt_forward(ctypes.c_void_p(x.data_ptr()), ctypes.c_int64(B), ctypes.c_int64(N), ctypes.c_int64(N),
-                                     c_taps, F, 8, 0, ctypes.c_float(2.0), 1, ctypes.c_float(1e-12), 0,
+                                     c_taps, F, 8, 0, ctypes.c_float(2.0), 0 if raw else 1, ctypes.c_float(1e-12), 0,
                                      ctypes.c_void_p(out.data_ptr()), None, stream)
             assert rc == 0
         torch.cuda.synchronize()
