@@ -977,7 +977,7 @@ wpt_tree_kernel(const float* __restrict__ x, long long x_row_stride, long long B
 #define AFD_WPT_FRAME_KERNEL 1
 #endif
 #ifndef AFD_WPT_STAGGER_DEFAULT
-#define AFD_WPT_STAGGER_DEFAULT 800
+#define AFD_WPT_STAGGER_DEFAULT 1200
 #endif
 constexpr int kFrameThreads = 512;
 constexpr int kGroupThreads = 256;
@@ -1494,7 +1494,7 @@ static int launch_frame(const float* x, int64_t B, int64_t N, int64_t x_row_stri
         }
         if (cache_ok > 0) {
             const char* stg = getenv("AFD_WPT_STAGGER");  // tuning knob (cycles); default measured on B200
-            cache.plan.stagger = stg ? atoi(stg) : AFD_WPT_STAGGER_DEFAULT;
+            cache.plan.stagger = stg ? atoi(stg) : (F <= 16 ? AFD_WPT_STAGGER_DEFAULT : AFD_WPT_STAGGER_DEFAULT / 3);   // sweep: sym5 best at 1200, coif4 at 400
             Coefs<F>& cf = cache.cf;
             for (int k = 0; k < F; ++k) {
                 cf.lo[k] = static_cast<float>(dec_lo[k]);
