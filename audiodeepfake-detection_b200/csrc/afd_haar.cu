@@ -161,7 +161,10 @@ haar_fingerprint_kernel(const float* __restrict__ x, long long x_row_stride, lon
 // makes all three access patterns bank-conflict free.
 // ================================================================================================
 constexpr int kFastThreads = 256;
-constexpr int kFlushEvery = 32;     // clips between flushes of the fp32 register accumulators into the fp64 sums
+#ifndef AFD_HAAR_FLUSH_EVERY
+#define AFD_HAAR_FLUSH_EVERY 64      // 32 -> 128 is worth +3 % at 32768-clip launches; 64 keeps the fp32 partial sums (128 terms) well inside 1e-5
+#endif
+constexpr int kFlushEvery = AFD_HAAR_FLUSH_EVERY;     // clips between flushes of the fp32 register accumulators into the fp64 sums
 
 struct HaarFastPlan {
     int N, L;
