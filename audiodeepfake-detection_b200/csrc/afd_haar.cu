@@ -17,6 +17,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <utility>
+
 #include "afd_common.cuh"
 
 namespace afd {
@@ -586,6 +588,68 @@ haar_stream_kernel(const float* __restrict__ x, long long x_row_stride, long lon
     if (since_flush) flush();
 }
 
+// Shared-memory accesses by 32-bit shared address + compile-time byte offset (volatile: program order is kept).  The linear
+// kernel forms its XOR-swizzled addresses as (aligned base ^ small constant), one LOP3 per access instead of XOR + scale + add.
+template <int IMM>
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(a), "n"(IMM));
+    return v;
+}
+template <int IMM>
+__device__ __forceinline__ void sts64(uint32_t a, float x, float y) {
+    asm volatile("st.shared.v2.f32 [%0+%1], {%2, %3};" ::"r"(a), "n"(IMM), "f"(x), "f"(y) : "memory");
+}
+template <int IMM>
+__device__ __forceinline__ float lds32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(IMM));
+    return v;
+}
+template <int IMM>
+__device__ __forceinline__ void sts32(uint32_t a, float x) {
+    asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(a), "n"(IMM), "f"(x) : "memory");
+}
+
+template <int SB, int... J>
+__device__ __forceinline__ void linear_b_load(uint32_t tl, float (&v)[32], std::integer_sequence<int, J...>) {
+    ((v[J] = lds32<SB + 128 * J>(tl ^ (8u * J)), v[J + 16] = lds32<SB + 128 * (J + 16)>(tl ^ (8u * J))), ...);
+}
+template <int SB, int... M>
+__device__ __forceinline__ void linear_b_store(uint32_t ts, const float (&v)[32], std::integer_sequence<int, M...>) {
+    ((sts32<SB>(ts ^ (128u * M), v[M]), sts32<SB + 2048>(ts ^ (128u * M), v[M + 16])), ...);
+}
+
+// Passes A and B of one 32-row block of the linear layout (see haar_linear_kernel), SH = the clip's shift in floats (0 / 2).
+// `blk` = shared address of the block's first float WITHOUT the shift (4096-byte aligned), rows_valid = rows to transform.
+template <int SH>
+__device__ __forceinline__ void haar_linear_block(uint32_t blk, int lane, int rows_valid) {
+    constexpr int SB = 4 * SH;                              // shift in bytes: an immediate of every access
+    const int k = lane & 15;
+    if (lane < rows_valid) {                                // pass A: lane = row, float2 column u ^ k in step u
+        float v[32];
+        const uint32_t t = (blk + 128u * lane) ^ (8u * k);  // row base is 128-byte aligned: base + 8 (u ^ k) = (base ^ 8k) ^ 8u
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const float2 q2 = lds64<SB>(t ^ (8u * u));
+            v[2 * u] = q2.x; v[2 * u + 1] = q2.y;
+        }
+        haar_stage<1>(v); haar_stage<2>(v); haar_stage<4>(v); haar_stage<8>(v); haar_stage<16>(v);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) sts64<SB>(t ^ (8u * u), v[2 * u], v[2 * u + 1]);
+    }
+    __syncwarp();
+    {                                                       // pass B: lane = level-5 node c, the block's 32 elements (rows)
+        float v[32];
+        const uint32_t tl = blk + 4u * lane;                // float (lane ^ 2 (j & 15)) of row j: (blk + 4 lane) ^ 8 (j & 15) + 128 j
+        linear_b_load<SB>(tl, v, std::make_integer_sequence<int, 16>{});
+        haar_stage<1>(v); haar_stage<2>(v); haar_stage<4>(v); haar_stage<8>(v); haar_stage<16>(v);
+        __syncwarp();                                       // every lane has read the tile before anybody overwrites it
+        const uint32_t ts = tl ^ (128u * (lane >> 1));      // row (m & 16) | ((m ^ hl) & 15), column lane (blk is 4096-byte aligned)
+        linear_b_store<SB>(ts, v, std::make_integer_sequence<int, 16>{});
+    }
+}
+
 // ================================================================================================
 // Linear-layout variant (r2): the streaming kernel above still spends a quarter of its warps on issuing cp.async (each
 // LDGSTS occupies its warp for ~90 cycles, and the copies crowd the same LSU queue the workers' LDS / STS go through).
@@ -662,9 +726,10 @@ haar_linear_kernel(const float* __restrict__ x, long long x_row_stride, long lon
         }
     };
 
-    float* const buf0 = smem_h;
-    float* const buf1 = smem_h + sp.buf_floats;
-    const uint32_t mbar0 = static_cast<uint32_t>(__cvta_generic_to_shared(smem_h + 2 * sp.buf_floats));
+    // the clip buffers are 4096-byte aligned (the XOR addressing of haar_linear_block relies on it)
+    float* const buf0 = smem_h + ((4096u - (static_cast<uint32_t>(__cvta_generic_to_shared(smem_h)) & 4095u)) & 4095u) / 4;
+    float* const buf1 = buf0 + sp.buf_floats;
+    const uint32_t mbar0 = static_cast<uint32_t>(__cvta_generic_to_shared(buf0 + 2 * sp.buf_floats));
     auto mbar = [&](int bufi, int c) { return mbar0 + 8u * static_cast<uint32_t>(bufi * kLinChunks + c); };
     if (tid < 2 * kLinChunks) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar0 + 8u * tid), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -729,32 +794,10 @@ haar_linear_kernel(const float* __restrict__ x, long long x_row_stride, long lon
             for (int e = 0; e < plan.extB; ++e) lin[32 * (n5 + e) + lane] = lin[32 * plan.tabB[e] + lane];
             __syncwarp();
         }
-        const int r = 32 * b + lane;                        // pass A: lane = row, float2 column u ^ k in step u
-        const int k = lane & 15;
-        if (r < n5 + plan.extB) {
-            float v[32];
-            float2* rowp = reinterpret_cast<float2*>(lin + 32 * r);
-#pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const float2 q2 = rowp[u ^ k];
-                v[2 * u] = q2.x; v[2 * u + 1] = q2.y;
-            }
-            haar_stage<1>(v); haar_stage<2>(v); haar_stage<4>(v); haar_stage<8>(v); haar_stage<16>(v);
-#pragma unroll
-            for (int u = 0; u < 16; ++u) rowp[u ^ k] = make_float2(v[2 * u], v[2 * u + 1]);
-        }
-        __syncwarp();
-        {                                                   // pass B: lane = level-5 node c, the block's 32 elements (rows)
-            float v[32];
-            float* base = lin + 1024 * b;
-            const int hl = lane >> 1;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = base[32 * j + (lane ^ ((j & 15) << 1))];
-            haar_stage<1>(v); haar_stage<2>(v); haar_stage<4>(v); haar_stage<8>(v); haar_stage<16>(v);
-            __syncwarp();                                   // every lane has read the tile before anybody overwrites it
-#pragma unroll
-            for (int m = 0; m < 32; ++m) base[32 * ((m & 16) | ((m ^ hl) & 15)) + lane] = v[m];
-        }
+        const uint32_t blk = static_cast<uint32_t>(__cvta_generic_to_shared(buf)) + 4096u * b;
+        const int rows_valid = n5 + plan.extB - 32 * b;     // >= 32 for every block but the last
+        if (sh) haar_linear_block<2>(blk, lane, rows_valid);
+        else haar_linear_block<0>(blk, lane, rows_valid);
     };
 
     int cur = 0;
@@ -880,7 +923,7 @@ static bool make_linear_plan(const HaarFastPlan& fp, HaarLinearPlan* lp) {
     for (int e = 0; e < fp.extA; ++e)
         if ((fp.tabA[e] >> 10) != lp->ext_block) return false;
     if (lp->ext_block != fp.n10 - 1) return false;                        // the tail lives in the last block (and last chunk)
-    lp->buf_floats = (1024 * fp.n10 + 2 + 31) / 32 * 32;                  // linear clip incl. appended rows, + shift; 128-byte multiple
+    lp->buf_floats = (1024 * fp.n10 + 2 + 1023) / 1024 * 1024;            // linear clip incl. appended rows, + shift; 4096-byte multiple
     for (int c = 0; c <= kLinChunks; ++c) lp->chunk_first[c] = static_cast<int>(static_cast<long long>(fp.n10) * c / kLinChunks);
     return make_stream_schedule(fp.n10, kLinWarps, kLinGroups < kMaxGroupsPerWarp ? kLinGroups : kMaxGroupsPerWarp, lp->blocks, lp->groups);
 }
@@ -988,10 +1031,10 @@ extern "C" int afd_haar_fingerprint_accum(const float* x, int64_t B, int64_t N, 
         const char* impl = getenv("AFD_HAAR_IMPL");       // "stream" / "fast": the earlier kernels (A/B, cross-checks)
         HaarLinearPlan lp;
         if (!impl && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_row_stride & 1) == 0 && make_linear_plan(fp, &lp) &&
-            2 * 4ull * lp.buf_floats + 8 * 2 * kLinChunks <= static_cast<size_t>(kMaxSmemPerCta)) {
+            2 * 4ull * lp.buf_floats + 8 * 2 * kLinChunks + 4096 <= static_cast<size_t>(kMaxSmemPerCta)) {
             long long grid = sms;
             if (grid > B) grid = B;
-            const size_t lsmem = 2 * 4ull * lp.buf_floats + 8 * 2 * kLinChunks;
+            const size_t lsmem = 2 * 4ull * lp.buf_floats + 8 * 2 * kLinChunks + 4096;      // + alignment slack
 #define AFD_HAAR_LINEAR(KK, HH)                                                                                      \
             {                                                                                                        \
                 static thread_local bool configured[16] = {false};                                                   \
