@@ -155,6 +155,14 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_ld4(uint32_t taddr, float (&v)[4]) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, no swizzle, version 1 (sm_100) shared-memory matrix descriptor
@@ -272,10 +280,51 @@ __device__ __forceinline__ float finish(float re, float im, const Params& p) {
 
 // Epilogue of one unit for the warps of k2 half KH: accumulator columns -> output tile.
 // Accumulator block of a part (Re at +0, Im at +96): columns [0, 48) = A_hi B_hi + A_lo B_hi, [48, 96) = A_hi B_lo.
+#ifndef AFD_TC_EPI_PIPELINED
+#define AFD_TC_EPI_PIPELINED 0      // r2: measured, no effect (347.4 vs 346.9 us, bit-identical): the TMEM load latency is not what the epilogue waits for
+#endif
 template <int MODE, int KH>
 __device__ __forceinline__ void combine(uint32_t taddr, uint32_t bar_d_empty, float* __restrict__ orow, const uint32_t (&binpk)[5],
                                         bool lane_live, int h, const Params& p) {
     constexpr int kLo = KH ? 19 : 0, kHi = KH ? 36 : 18;
+#if AFD_TC_EPI_PIPELINED
+    // Six rounds of four accumulator columns, the tensor-memory loads of round r + 1 in flight while round r is finished
+    // (three rounds of eight columns exposed the full tcgen05.ld latency three times per unit and warp).
+    float re[2][4], im[2][4], re2[2][4], im2[2][4];
+    constexpr int kBase = KH ? 16 : 0;
+    tc_ld4(taddr + kBase, re[0]);
+    tc_ld4(taddr + 48 + kBase, re2[0]);
+    tc_ld4(taddr + 96 + kBase, im[0]);
+    tc_ld4(taddr + 144 + kBase, im2[0]);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        const int col0 = kBase + 4 * r;
+        tc_ld_wait();
+        if (r < 5) {
+            tc_ld4(taddr + col0 + 4, re[(r + 1) & 1]);
+            tc_ld4(taddr + 48 + col0 + 4, re2[(r + 1) & 1]);
+            tc_ld4(taddr + 96 + col0 + 4, im[(r + 1) & 1]);
+            tc_ld4(taddr + 144 + col0 + 4, im2[(r + 1) & 1]);
+        } else {                               // every accumulator of the unit is in registers: release the buffer
+            tc_fence_before();
+            mbar_arrive(bar_d_empty);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k2 = col0 + i;
+            if (k2 < kLo || k2 > kHi) continue;
+            if (AFD_KO(2) && k2 != kLo) continue;
+            const float rr = re[r & 1][i] + re2[r & 1][i], q = im[r & 1][i] + im2[r & 1][i];
+            const float pre = __shfl_xor_sync(0xffffffffu, rr, 16);
+            const float pim = __shfl_xor_sync(0xffffffffu, q, 16);
+            const float val = finish<MODE>(rr - pim, q + pre, p);
+            const int idx = k2 - kLo;
+            const uint32_t bin = (binpk[idx >> 2] >> (8 * (idx & 3))) & 255u;
+            const bool live = lane_live && !(h == 1 && k2 == 0);
+            if (live) orow[bin] = val;
+        }
+    }
+#else
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const int col0 = (KH ? 16 : 0) + 8 * c;
@@ -304,6 +353,7 @@ __device__ __forceinline__ void combine(uint32_t taddr, uint32_t bar_d_empty, fl
             if (live) orow[bin] = val;
         }
     }
+#endif
 }
 
 template <bool EXT, int MODE>
