@@ -6,7 +6,12 @@
 // for the low-pass h = dec_lo and the high-pass g = dec_hi, recursively to `level`, then orders the
 // leaves by Gray code, stacks them P-innermost and applies log(|c|^power + 1e-12).
 //
-// Design:
+// Two kernels share the work-item code below.  wpt_frame_kernel (r2, further down) serves every filter that has a usable
+// lattice when the whole tree fits one CTA: one 512-thread CTA per frame, level 1 as a lattice pass over the staged frame,
+// two 256-thread groups for the half trees.  wpt_tree_kernel (r1: two CTAs per frame, described next) serves the rest:
+// direct-form filters (F > 32, coif5), long frames, very deep trees.
+//
+// Design of wpt_tree_kernel:
 //   * One frame is handled by TWO persistent CTAs: CTA h (0/1) owns the sub-tree under the level-1 node
 //     'a'/'d' and applies only its own level-1 filter (direct form), so no FMA is duplicated; the second read of
 //     the frame is an L2 hit.  A half-tree needs ~100 KB of shared memory for the headline configs (level 8,
