@@ -419,12 +419,24 @@ __device__ __forceinline__ void load_window(const float* __restrict__ p, float (
     }
 }
 
-template <int F, int R, bool LAT, bool REFL>
+// The same window from an address that is only 8-byte aligned (frame kernel: a root staged with a 2-float shift)
+template <int NV>
+__device__ __forceinline__ void load_window_f2(const float* __restrict__ p, float (&w)[4 * NV]) {
+    const float2* src = reinterpret_cast<const float2*>(p);
+#pragma unroll
+    for (int v = 0; v < 2 * NV; ++v) {
+        const float2 q = src[v];
+        w[2 * v] = q.x; w[2 * v + 1] = q.y;
+    }
+}
+
+template <int F, int R, bool LAT, bool REFL, bool SH2 = false>
 __device__ __forceinline__ void filter_pair(const float* __restrict__ src, const Coefs<F>& cf, float (&lo)[R],
                                             float (&hi)[R], bool first, int jn) {
     using WN = Win<F, R>;
     float w[WN::WLEN];
-    load_window<WN::NV>(src, w);
+    if constexpr (SH2) load_window_f2<WN::NV>(src, w);
+    else load_window<WN::NV>(src, w);
     if constexpr (REFL && AFD_WPT_REFLECT_RIGHT) {
         if (jn < WN::W - 1) {              // the window crosses the node's end: x~[n-1+i] = x[n-1-i], i = 1 .. F-2 (+1)
             const unsigned padr = static_cast<unsigned>(F - 2 + ((jn + 1) & 1));     // jn = n + F - 3 - 2 k0: n odd <=> jn even
@@ -561,7 +573,7 @@ __device__ __forceinline__ void mirror_copy(float* __restrict__ base, int nodes,
 }
 
 // One stored tree level with uniform items (see AFD_WPT_UNIFORM): item = (node, chunk), lanes walk along a node.
-template <int F, int R, bool LAT>
+template <int F, int R, bool LAT, bool SH2 = false>
 __device__ __forceinline__ void mid_level_uniform(const float* __restrict__ in, float* __restrict__ out, const Pass& ps,
                                                   const Coefs<F>& cf, int tid = threadIdx.x, int nthr = kThreads) {
     constexpr int padl = F - 2;
@@ -572,7 +584,7 @@ __device__ __forceinline__ void mid_level_uniform(const float* __restrict__ in, 
         const int c = it - node * ps.C;
         const int k0 = c * R;
         float lo[R], hi[R];
-        filter_pair<F, R, LAT, true>(in + node * ps.in_stride + 2 * k0, cf, lo, hi, c == 0, 0);
+        filter_pair<F, R, LAT, true, SH2>(in + node * ps.in_stride + 2 * k0, cf, lo, hi, c == 0, 0);
         if (do_mul) scale_all<R>(lo, hi, ps.mul);
         float* d0 = out + (2 * node) * ps.out_stride + padl + k0;
         vec_store<R>(d0, lo);
@@ -991,6 +1003,57 @@ __device__ __forceinline__ void group_barrier(int group) {
     asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kGroupThreads) : "memory");
 }
 
+// Staging of a frame as the padded root node by ONE warp: a single bulk copy (TMA engine; no thread waits for it and nothing
+// enters the LSU queue -- the 5512 cp.async.16 of the first version kept the issuing group busy for 4.7 k cycles per frame,
+// 16 % of the step, in front of its last level) plus a few scalar copies.  Sample i of the frame sits at root[F - 2 + d + i];
+// d (0 or 2 floats) makes source and destination congruent mod 16 bytes (a frame is 88,200 B: odd frames are 8-byte aligned).
+// By threads: the samples in front of the first / behind the last whole 16-byte unit and the right reflect padding
+// x~[N-1+i] = x[N-1-i]; the left padding is never read (register reflection of the first item).
+template <int F>
+__device__ __forceinline__ int root_shift(const float* xg) {
+    const int a = static_cast<int>((reinterpret_cast<uintptr_t>(xg) & 15u) >> 2);       // 0 or 2 (host-checked)
+    return (a - (F - 2)) & 3;
+}
+template <int F>
+__device__ __forceinline__ void stage_root_bulk(const float* __restrict__ xg, float* __restrict__ root, int N, uint32_t bar, int lane) {
+    constexpr int padl = F - 2;
+    const int a = static_cast<int>((reinterpret_cast<uintptr_t>(xg) & 15u) >> 2);
+    const int d = (a - padl) & 3;
+    const int s0 = (4 - a) & 3;                             // first sample at a 16-byte boundary
+    const int units = (N - s0) >> 2;
+    float* const dst = root + padl + d;                     // position of sample 0
+    if (lane < s0) dst[lane] = __ldg(xg + lane);
+    for (int s = s0 + 4 * units + lane; s < N; s += 32) dst[s] = __ldg(xg + s);
+    const int padr = padl + 1 + 3;                          // right padding incl. the odd-length sample and the item over-read's first floats
+    for (int j = lane; j < padr && j < N - 1; j += 32) dst[N + j] = __ldg(xg + (N - 2 - j));
+    __syncwarp();
+    if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const uint32_t bytes = 16u * static_cast<uint32_t>(units);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        if (bytes)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst + s0))), "l"(xg + s0), "r"(bytes), "r"(bar) : "memory");
+    }
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+
+// Bulk staging pays for the short filters (sym5: -3 % time); for coif4 it is 1.9 % SLOWER than the cp.async staging (the
+// issue time it removes was hidden behind the other group's work, and half of the frames pay 8-byte window loads in level 1).
+#ifndef AFD_WPT_BULK_ROOT_MAXF
+#define AFD_WPT_BULK_ROOT_MAXF 16
+#endif
+template <int F>
+struct BulkRoot {
+    static constexpr bool value = F <= AFD_WPT_BULK_ROOT_MAXF;
+};
+
 template <int F, int R0, int RA, int RB, int RLA, int RLB, bool EXT>
 __global__ void __launch_bounds__(kFrameThreads, 1)
 wpt_frame_kernel(const float* __restrict__ x, long long x_row_stride, long long B, float* __restrict__ out,
@@ -1011,9 +1074,16 @@ wpt_frame_kernel(const float* __restrict__ x, long long x_row_stride, long long 
     bool first = true;
     // three words behind the planned regions: groups that have finished with region B (monotonic count), and per group
     // whether it was the second one to arrive
-    unsigned int& s_arrivals = *reinterpret_cast<unsigned int*>(smem + plan.smem_floats);
-    int* const s_second = reinterpret_cast<int*>(smem + plan.smem_floats + 1);
-    if (tid == 0) s_arrivals = 0;
+    const uint32_t root_bar = static_cast<uint32_t>(__cvta_generic_to_shared(smem + plan.smem_floats));    // mbarrier: the root's bulk copy
+    unsigned int& s_arrivals = *reinterpret_cast<unsigned int*>(smem + plan.smem_floats + 2);
+    int* const s_second = reinterpret_cast<int*>(smem + plan.smem_floats + 3);
+    if (tid == 0) {
+        s_arrivals = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(root_bar), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t root_parity = 0;
     ThreadStats ts;
     ts.s[0] = ts.s[1] = ts.q[0] = ts.q[1] = ts.m[0] = ts.m[1] = 0.f;
     ts.fs[0] = ts.fs[1] = ts.fq[0] = ts.fq[1] = 0.f;
@@ -1026,14 +1096,22 @@ wpt_frame_kernel(const float* __restrict__ x, long long x_row_stride, long long 
     for (long long b = blockIdx.x; b < B; b += gridDim.x) {
         const float* xg = x + b * x_row_stride;
         const long long nb = b + gridDim.x;
+        constexpr bool kBulk = BulkRoot<F>::value;
         if (!prefetched) {
             if (!first) __syncthreads();                   // region B may still be read by a group's last passes
-            issue_chunk<F>(xg, root, 0, plan, kFrameThreads);
+            if constexpr (kBulk) { if (tid < 32) stage_root_bulk<F>(xg, root, plan.N, root_bar, tid); }
+            else issue_chunk<F>(xg, root, 0, plan, kFrameThreads);
         }
         first = false;
         prefetched = false;
-        cp_async_wait<0>();
-        __syncthreads();
+        if constexpr (kBulk) {
+            mbar_wait_parity(root_bar, root_parity);       // the bulk copy has landed ...
+            root_parity ^= 1u;
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();                                   // ... and so have the staging warp's scalar copies
+        const bool root_sh2 = kBulk && root_shift<F>(xg) != 0;
         AFD_PHASE_MARK(0);
         float* out_b = out + b * C * static_cast<long long>(T) * P;
         // ---------------------------------------------------------------- passes
@@ -1042,7 +1120,8 @@ wpt_frame_kernel(const float* __restrict__ x, long long x_row_stride, long long 
             if (pi == 0) {
                 // level 1: the root's two children, all 512 threads
                 if (ps.kind == 0) {
-                    mid_level_uniform<F, R0, true>(smem + ps.in_off, smem + ps.out_off, ps, cf, tid, kFrameThreads);
+                    if (kBulk && root_sh2) mid_level_uniform<F, R0, true, kBulk>(smem + ps.in_off + 2, smem + ps.out_off, ps, cf, tid, kFrameThreads);
+                    else mid_level_uniform<F, R0, true, false>(smem + ps.in_off, smem + ps.out_off, ps, cf, tid, kFrameThreads);
                     __syncthreads();
                     mirror_copy<F>(smem + ps.out_off, 2, ps.n_out, ps.out_stride, tid, kFrameThreads);
                     __syncthreads();
@@ -1054,8 +1133,7 @@ wpt_frame_kernel(const float* __restrict__ x, long long x_row_stride, long long 
                         while (clock64() - t0 < plan.stagger) { }
                     }
                 } else {
-                    // L == 1: the two leaves straight from the root; group g keeps leaf g
-                    if (ps.prefetch && nb < B) { issue_chunk<F>(x + nb * x_row_stride, root, 0, plan, kFrameThreads); prefetched = true; }
+                    // L == 1 is served by the two-CTA kernel (make_frame_plan refuses it)
                     last_level<F, RLA, true, EXT, true>(smem + ps.in_off, ps, T, 0, out_b, P, cf, ep, ts, tid, kFrameThreads);
                 }
                 AFD_PHASE_MARK(1);
@@ -1077,7 +1155,8 @@ wpt_frame_kernel(const float* __restrict__ x, long long x_row_stride, long long 
                     if (gt == 0) s_second[group] = static_cast<int>(atomicAdd(&s_arrivals, 1u) & 1u);
                     group_barrier(group);
                     if (nb < B) {
-                        if (s_second[group]) issue_chunk<F>(x + nb * x_row_stride, root, 0, plan, kGroupThreads, gt);
+                        if constexpr (kBulk) { if (s_second[group] && gt < 32) stage_root_bulk<F>(x + nb * x_row_stride, root, plan.N, root_bar, gt); }
+                        else { if (s_second[group]) issue_chunk<F>(x + nb * x_row_stride, root, 0, plan, kGroupThreads, gt); }
                         prefetched = true;
                     }
                 }
@@ -1386,7 +1465,8 @@ static int make_frame_plan(int64_t N, int F, int L, int R0, const Tuning& tu, do
     p->nch = 1;
     const int c1 = (n[1] + R0 - 1) / R0;
     if (c1 > kFrameThreads) return AFD_ERR_UNSUPPORTED;
-    p->buf_floats = round_up(2 * c1 * R0 + F + 8, 4);
+    if (L < 2) return AFD_ERR_UNSUPPORTED;                   // a single level: the two-CTA kernel's special case
+    p->buf_floats = round_up(2 * c1 * R0 + F + 8 + 4, 4);      // + the root's alignment shift
     stride[0] = p->buf_floats;
     for (int l = 1; l < L; ++l) {
         const int r_prod = l == 1 ? R0 : (tu.RA > tu.RB ? tu.RA : tu.RB);
@@ -1421,7 +1501,7 @@ static int make_frame_plan(int64_t N, int F, int L, int R0, const Tuning& tu, do
     const int root_floats = p->buf_floats + tail;
     p->region_b = 2 * half[0];
     p->smem_floats = p->region_b + (2 * half[1] > root_floats ? 2 * half[1] : round_up(root_floats, 4));
-    if (4LL * (p->smem_floats + 4) > kMaxSmemPerCta) return AFD_ERR_UNSUPPORTED;      // + the kernel's three sync words
+    if (4LL * (p->smem_floats + 8) > kMaxSmemPerCta) return AFD_ERR_UNSUPPORTED;      // + the kernel's mbarrier and sync words
     auto region = [&](int l) { return (l & 1) ? 0 : p->region_b; };
     double pending = 1.0;
     auto stored_mul = [&]() {
@@ -1524,12 +1604,14 @@ static int launch_frame(const float* x, int64_t B, int64_t N, int64_t x_row_stri
         cache.valid = true;
     }
     if (cache_ok < 0) return AFD_OK;                       // not taken: the caller falls back to the two-CTA kernel
+    // a root staged by a bulk copy: every frame must start on an 8-byte boundary (16-byte units, 0 or 2 floats of shift)
+    if (BulkRoot<F>::value && ((reinterpret_cast<uintptr_t>(x) & 7) != 0 || (x_row_stride & 1) != 0)) return AFD_OK;
     *taken = true;
     Epilogue epk = ep;
     epk.stats_simple = cache.stats_simple;
     long long grid = cache.sms;
     if (grid > B) grid = B;
-    kern<<<static_cast<unsigned>(grid), kFrameThreads, 4 * (cache.plan.smem_floats + 4), stream>>>(
+    kern<<<static_cast<unsigned>(grid), kFrameThreads, 4 * (cache.plan.smem_floats + 8), stream>>>(
         x, static_cast<long long>(x_row_stride), static_cast<long long>(B), out, cache.plan, cache.cf, epk);
     AFD_CUDA_TRY(cudaGetLastError());
 #if AFD_WPT_PHASE_TIMING

@@ -117,6 +117,16 @@ def test_strided_rows_and_odd_alignment(cuda_device):
     assert not view.is_contiguous()
     w = afd.Wavelet("coif4")
     assert torch.equal(afd.wavelet_packet_features(view, w, 8), afd.wavelet_packet_features(view.contiguous(), w, 8))
+    # short filters stage the frame with a 16-byte bulk copy: 8-byte aligned rows (even stride, any even offset) take the same
+    # kernel with a 2-float shift and give the same bits; rows that are only 4-byte aligned are served by the two-CTA kernel,
+    # whose level 1 runs in the direct form instead of the lattice: same values to fp32 rounding
+    big8 = torch.randn(6, 22050 + 8, device=cuda_device, generator=g) * 0.1
+    s5 = afd.Wavelet("sym5")
+    for off in (2, 4, 6):
+        v8 = big8[:, off:off + 22050]
+        assert torch.equal(afd.wavelet_packet_features(v8, s5, 8), afd.wavelet_packet_features(v8.contiguous(), s5, 8))
+    a, b = afd.wavelet_packet_features(view, s5, 8), afd.wavelet_packet_features(view.contiguous(), s5, 8)
+    assert float((a - b).abs().max() / b.abs().max()) < 1e-6
     assert torch.equal(afd.stft_power_features(view), afd.stft_power_features(view.contiguous()))
     assert torch.allclose(afd.haar_fingerprint(view), afd.haar_fingerprint(view.contiguous()), rtol=1e-12)
 
