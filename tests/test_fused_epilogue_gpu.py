@@ -185,3 +185,32 @@ def test_calc_normalization_and_fused_normalize(transform):
     assert float((ident(fused) - two_step).abs().max()) < 1e-5
     assert fused.stride() == two_step.stride()
     assert abs(float(fused.mean())) < 1e-4 and abs(float(fused.std()) - 1.0) < 1e-3
+
+
+def test_get_transforms_writes_and_reloads_the_reference_norm_cache(tmp_path):
+    """reference wavelet_math.py:349-367, :449-450: normalization=True computes the statistics over the training batches
+    (args.norm_batches stands in for the reference's DataLoader), caches them as <norm_dir>_mean_std.pkl in the reference's
+    own pickle format, and the next call -- with or without normalization -- loads that file."""
+    import os
+    import pickle
+
+    from audiodeepfake_detection_b200 import wavelet_math
+
+    x = torch.from_numpy(_frames(8, seed=21)).cuda().unsqueeze(1)
+    args = _Args(transform="packets", num_of_scales=256, hop_length=220, log_scale=True, power=2.0, wavelet="sym5",
+                 loss_less="False", features="none", block_norm=False, mean=[0.0], std=[1.0],
+                 log_dir=str(tmp_path), data_path="/data/run1", only_use=["ljspeech", "melgan"], sample_rate=22050, seconds=1,
+                 norm_batches=[{"audio": x[:4]}, {"audio": x[4:]}])
+    tr, norm = afd.get_transforms(args, "none", "cuda", True, verbose=False)
+    path = wavelet_math.norm_cache_prefix(args) + "_mean_std.pkl"
+    assert os.path.exists(path)
+    with open(path, "rb") as fh:
+        mean, std = pickle.load(fh)                       # plain numpy arrays, as the reference writes them
+    assert abs(float(mean) - float(norm[0].mean)) < 1e-6 and abs(float(std) - float(norm[0].std)) < 1e-6
+    feats, aux = tr(x)
+    assert len(aux) == 256                                # compute_welford=True as in the reference (:304)
+    want_mean, want_std = afd.normalization_stats([feats])
+    assert abs(float(mean) - float(want_mean)) < 1e-4 and abs(float(std) - float(want_std)) < 1e-4
+    args2 = _Args({k: v for k, v in args.items() if k != "norm_batches"})
+    _, norm2 = afd.get_transforms(args2, "none", "cuda", False, verbose=False)          # loads the cache
+    assert float(norm2[0].mean) == float(norm[0].mean) and float(norm2[0].std) == float(norm[0].std)
