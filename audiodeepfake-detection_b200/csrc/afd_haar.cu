@@ -666,16 +666,22 @@ __device__ __forceinline__ void haar_linear_block(uint32_t blk, int lane, int ro
 // register m to row m ^ (c >> 1), plain column c: signs and permutations cancel with no extra arithmetic, and pass C reads a
 // plain [element][node] array.  Odd clips (88,200 B apart: 8-byte aligned) are copied from 8 bytes earlier; all indices are
 // then shifted by sh = 2 floats, which the float2 accesses of pass A and the scalar accesses of passes B / C absorb.
-// All 16 warps work; blocks and node groups are dealt by the same greedy schedule.
+// All 18 warps work; blocks and node groups are dealt by the same greedy schedule (measured costs: 1.35 : 1).
 // ================================================================================================
 constexpr int kLinChunks = 4;             // bulk copies (and mbarriers) per clip
+#ifndef AFD_HAAR_BLOCK_COST
+#define AFD_HAAR_BLOCK_COST 1.35
+#endif
 #ifndef AFD_HAAR_LIN_THREADS
-#define AFD_HAAR_LIN_THREADS 512
+#define AFD_HAAR_LIN_THREADS 576     // 18 warps: 22 blocks + 32 node groups split 4 x (2 blocks + 1 group) / 14 x (1 block + 2 groups); 512: +5 % time, 640 / 704: spills
 #endif
 constexpr int kLinThreads = AFD_HAAR_LIN_THREADS;
 constexpr int kLinWarps = kLinThreads / 32;
 constexpr int kLinMaxWarps = 32;
-constexpr int kLinGroups = (32 + kLinWarps - 1) / kLinWarps + (kLinWarps < 22 ? 1 : 0);   // node groups a warp may own (acc registers)
+#ifndef AFD_HAAR_LIN_GROUPS
+#define AFD_HAAR_LIN_GROUPS (AFD_HAAR_LIN_THREADS / 32 >= 18 ? 2 : 3)
+#endif
+constexpr int kLinGroups = AFD_HAAR_LIN_GROUPS;   // node groups a warp may own (acc registers)
 
 struct HaarLinearPlan {
     HaarFastPlan fast;
@@ -884,7 +890,8 @@ haar_linear_kernel(const float* __restrict__ x, long long x_row_stride, long lon
     if (since_flush) flush();
 }
 
-static bool make_stream_schedule(int n10, int workers, int max_groups, signed char (*blocks)[kMaxBlocksPerWarp], signed char (*groups)[kMaxGroupsPerWarp]) {
+static bool make_stream_schedule(int n10, int workers, int max_groups, signed char (*blocks)[kMaxBlocksPerWarp], signed char (*groups)[kMaxGroupsPerWarp],
+                                 double block_cost) {
     if (n10 > workers * kMaxBlocksPerWarp || 32 > workers * max_groups) return false;
     double load[kLinMaxWarps] = {0};
     int nb[kLinMaxWarps] = {0}, ng[kLinMaxWarps] = {0};
@@ -903,7 +910,7 @@ static bool make_stream_schedule(int n10, int workers, int max_groups, signed ch
         const int w = least(nb, kMaxBlocksPerWarp);
         if (w < 0) return false;
         blocks[w][nb[w]++] = static_cast<signed char>(b);
-        load[w] += 2.4;
+        load[w] += block_cost;
     }
     for (int g = 0; g < 32; ++g) {
         const int w = least(ng, max_groups);
@@ -925,7 +932,9 @@ static bool make_linear_plan(const HaarFastPlan& fp, HaarLinearPlan* lp) {
     if (lp->ext_block != fp.n10 - 1) return false;                        // the tail lives in the last block (and last chunk)
     lp->buf_floats = (1024 * fp.n10 + 2 + 1023) / 1024 * 1024;            // linear clip incl. appended rows, + shift; 4096-byte multiple
     for (int c = 0; c <= kLinChunks; ++c) lp->chunk_first[c] = static_cast<int>(static_cast<long long>(fp.n10) * c / kLinChunks);
-    return make_stream_schedule(fp.n10, kLinWarps, kLinGroups < kMaxGroupsPerWarp ? kLinGroups : kMaxGroupsPerWarp, lp->blocks, lp->groups);
+    // measured (phase table): a block's passes A + B take ~1.75 k cycles, a node group's pass C ~1.3 k
+    return make_stream_schedule(fp.n10, kLinWarps, kLinGroups < kMaxGroupsPerWarp ? kLinGroups : kMaxGroupsPerWarp, lp->blocks, lp->groups,
+                                AFD_HAAR_BLOCK_COST);
 }
 
 // Greedy schedule: blocks (cost 2.4) then node groups (cost 1) to the least loaded warp.
