@@ -81,3 +81,13 @@ def test_compute_fingerprint_rfft_surface():
     assert freqs.shape == fp.shape == (11026,) and float(freqs[-1]) == 11025.0 and fp.is_cuda
     with pytest.raises(ValueError):
         afd.SpectrumFingerprintAccumulator(22051)
+
+
+def test_large_batch_matches_oracle(cuda_device):
+    """More clips than SMs x 2 (the streaming kernel's double-buffered walk, odd / even clip alignment): against the oracle."""
+    rng = np.random.default_rng(77)
+    x = (rng.standard_normal((700, 22050)) * 0.1).astype(np.float32)
+    got = afd.haar_fingerprint(torch.from_numpy(x).to(cuda_device), 14).cpu().numpy()
+    sums, count = oracle.haar_fingerprint_sums(x.astype(np.float64), 14, dtype=np.float64)
+    assert count == 700 * 2
+    assert np.max(np.abs(got - sums / count)) < 1e-5 * np.max(sums / count)

@@ -158,3 +158,14 @@ def test_pfa511_log_and_power(impl, cuda_device, monkeypatch):
     assert np.max(np.abs(logs - want)[big]) < LOG_TOL * np.max(np.abs(want))
     mag = afd.stft_power_features(xt, 511, 220, 1.0, False)[:, 0].cpu().numpy()
     assert _rel(mag, np.sqrt(truth)) < 1e-4
+
+
+def test_full_batch_sampled_signals_match_dft64(cuda_device):
+    """BASELINE batch size (4096 signals): a sample of signals against the fp64 DFT."""
+    g = torch.Generator(device="cuda").manual_seed(12)
+    x = torch.randn(4096, 22050, device=cuda_device, generator=g) * 0.1
+    spec = afd.stft_power_features(x)                                   # [B, 1, frames, bins]
+    pick = np.concatenate([np.random.default_rng(6).choice(4096, size=8, replace=False), [0, 4095]])
+    want = ptwt_like.stft_power_dft64(x[pick].cpu().numpy().astype(np.float64)).transpose(0, 2, 1)
+    got = spec[pick, 0].cpu().numpy()
+    assert got.shape == want.shape and _rel(got, want) < TOL

@@ -139,3 +139,24 @@ def test_linearity_and_determinism_full_size(cuda_device):
     # every frame is independent of its batch neighbours: frame 1234 alone gives the same bits
     alone = afd.wavelet_packet_features(x[1234:1235].clone(), w, 8)
     assert torch.equal(alone[0], fx[1234])
+
+
+@pytest.mark.parametrize("name", ["sym5", "coif4"])
+def test_full_batch_sampled_frames_match_oracle(name):
+    """BASELINE batch size (4096 frames: every CTA of the frame kernel walks ~28 frames, prefetching the next one while
+    its last level runs): a random sample of frames against the fp64 oracle, raw and log-scaled."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(4096, 1, 22050, device="cuda", generator=g) * 0.1
+    raw = afd.wavelet_packet_features(x, Wavelet(name), 8)
+    logf = afd.wavelet_packet_features(x, Wavelet(name), 8, log_scale=True)
+    torch.cuda.synchronize()
+    pick = np.random.default_rng(5).choice(4096, size=12, replace=False)
+    pick = np.concatenate([pick, [0, 147, 148, 4095]])            # first / last frame of a CTA's walk on a 148-SM part
+    xs = x[pick, 0].cpu().numpy().astype(np.float64)
+    want = oracle.packet_features(xs, ORACLE_TAPS[name], 8, dtype=np.float64)
+    got = raw[pick].cpu().numpy()
+    assert got.shape == want.shape and _rel(got, want) < COEF_TOL
+    want_log = np.log(want * want + 1e-12)
+    got_log = logf[pick].cpu().numpy()
+    big = np.abs(want) > 1e-2 * np.max(np.abs(want))
+    assert np.max(np.abs(got_log - want_log)[big]) < LOG_TOL * np.max(np.abs(want_log))
