@@ -562,13 +562,26 @@ def get_transforms(args, features: str, device: str, normalization: bool, pbar: 
     return transforms, normalize
 
 
-def calc_normalization(transforms: torch.nn.Sequential, audio_batches) -> tuple:
+def merge_moments_across_ranks(moments: torch.Tensor, count: int, group=None) -> tuple[torch.Tensor, int]:
+    """Sum the per-rank feature moments ``[C, 2]`` (sum, sum of squares) and element counts over the ranks of
+    ``torch.distributed`` (one all-reduce of 2C + 1 fp64): every rank gets the statistics of the whole sharded set."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return moments, count
+    packed = torch.cat([moments.reshape(-1), torch.tensor([float(count)], dtype=torch.float64, device=moments.device)])
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    return packed[:-1].reshape(moments.shape), int(round(float(packed[-1])))
+
+
+def calc_normalization(transforms: torch.nn.Sequential, audio_batches, distributed: bool = False, group=None) -> tuple:
     """Mean / std of the features over ``audio_batches`` (reference wavelet_math.py:387-452, minus the dataset
     plumbing): returns ``(welford_dict, mean, std)`` like the reference, mean / std per channel.
 
     One statistics-only launch per batch: the kernels accumulate the feature sum / sum of squares in fp64 on the
     device (``feat_moments``) and never write the feature tensor, so the pass reads 88 KB per frame and writes
-    nothing."""
+    nothing.  The reference runs this pass over the WHOLE training set on every rank; with ``distributed=True`` each
+    rank passes its own shard of the batches and the moments meet in one all-reduce."""
     tr = transforms[0]
     dev = None
     moments, count, welford_dict = None, 0, None
@@ -595,6 +608,8 @@ def calc_normalization(transforms: torch.nn.Sequential, audio_batches) -> tuple:
         tr.feat_moments, tr.store, tr.fused_norm = saved
     if moments is None:
         raise ValueError("calc_normalization: no batches")
+    if distributed:
+        moments, count = merge_moments_across_ranks(moments, count, group)
     mean = moments[:, 0] / count
     std = torch.sqrt(torch.clamp(moments[:, 1] / count - mean * mean, min=0))
     return welford_dict, mean.float(), std.float()

@@ -48,6 +48,13 @@ def _worker(rank, world, port, tmp):
         feats = torch.arange(5 * 6, dtype=torch.float32).reshape(5, 1, 2, 3)
         back = gather_features(local_shard(feats).clone())
         assert torch.equal(back, feats)
+        # normalisation statistics of a sharded training set: per-rank moments + counts meet in one all-reduce
+        from audiodeepfake_detection_b200.wavelet_math import merge_moments_across_ranks
+        vals = torch.arange(1, 11, dtype=torch.float64)                # the "features" of the whole set
+        part = vals[:6] if rank == 0 else vals[6:]
+        mom = torch.stack([part.sum(), (part * part).sum()]).reshape(1, 2)
+        merged, n = merge_moments_across_ranks(mom, part.numel())
+        assert n == 10 and torch.allclose(merged, torch.tensor([[vals.sum(), (vals * vals).sum()]], dtype=torch.float64))
         open(os.path.join(tmp, f"ok{rank}"), "w").close()
     finally:
         dist.destroy_process_group()
