@@ -10,7 +10,10 @@
 
 namespace afd {
 
-constexpr int kSlots = 4;
+#ifndef AFD_HOST_SLOTS
+#define AFD_HOST_SLOTS 4
+#endif
+constexpr int kSlots = AFD_HOST_SLOTS;
 
 // Per-device pipeline state, created on first use and kept for the life of the process: streams and device
 // staging buffers are reused by every host-buffer call (cudaMalloc / cudaFree per call would serialise the
@@ -65,11 +68,15 @@ static int run_pipelined(const float* x_host, int64_t B, int64_t N, int64_t x_ro
             e = ensure(&pl->d_out[i], &pl->out_cap[i], sizeof(float) * chunk * out_row_floats);
         if (e != cudaSuccess) rc = cuda_fail(e, "pipeline slot allocation");
     }
+    // Ramp-up: the device-to-host copies (the longer direction for the feature tensors) cannot start before the first
+    // chunk's host-to-device copy and kernel are through, so the first chunks are small (chunk / 8, / 4, / 2) and the pipeline
+    // fills in ~1/8 of a chunk's copy time.
     int64_t done = 0;
     for (int64_t c = 0; rc == AFD_OK && done < B; ++c) {
         const int i = static_cast<int>(c % nslots);
         cudaStream_t s = pl->stream[i];
-        const int64_t nb = std::min(chunk, B - done);
+        const int64_t ramp = c < 3 ? std::max<int64_t>(chunk >> (3 - c), 1) : chunk;
+        const int64_t nb = std::min(ramp, B - done);
         cudaError_t e;
         if (x_row_stride == N)
             e = cudaMemcpyAsync(pl->d_in[i], x_host + done * N, sizeof(float) * nb * N, cudaMemcpyHostToDevice, s);
