@@ -95,6 +95,7 @@ struct WptPlan {
     int nch;                    // staging chunks per frame
     int npass;
     int smem_floats;            // total dynamic shared memory in floats
+    int root_split;             // frame kernel: root float index where group 1's half of region B starts (multiple of 4)
     int stagger;                // frame kernel: cycles group 1 idles after level 1 so that the groups run out of phase
     Pass pass[kMaxPasses];
 };
@@ -795,13 +796,16 @@ __device__ __forceinline__ void issue_chunk(const float* __restrict__ xg, float*
         const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(buf + (r_lo - s_start)));
         const int n = r_hi - r_lo;
         const unsigned mis = static_cast<unsigned>(reinterpret_cast<uintptr_t>(src)) | dst;
-        if ((mis & 15) == 0) {
-            const int units = n >> 2;
-            const char* s = src + 16 * tid;
-            uint32_t d = dst + 16 * tid;
+        if (((static_cast<unsigned>(reinterpret_cast<uintptr_t>(src)) ^ dst) & 15) == 0) {
+            // congruent modulo 16 bytes: single floats up to the first 16-byte boundary, 16-byte copies, single floats
+            const int head = min(n, static_cast<int>(((16u - (dst & 15u)) & 15u) >> 2));
+            const int units = (n - head) >> 2;
+            const char* s = src + 4 * head + 16 * tid;
+            uint32_t d = dst + 4 * head + 16 * tid;
             for (int i = tid; i < units; i += nthr, s += 16 * nthr, d += 16 * nthr)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(s));
-            if (tid < (n & 3)) cp_async_4(buf + (r_lo - s_start) + 4 * units + tid, xg + r_lo + 4 * units + tid);
+            if (tid < head) cp_async_4(buf + (r_lo - s_start) + tid, xg + r_lo + tid);
+            if (tid < n - head - 4 * units) cp_async_4(buf + (r_lo - s_start) + head + 4 * units + tid, xg + r_lo + head + 4 * units + tid);
         } else if ((mis & 7) == 0) {
             const int units = n >> 1;
             const char* s = src + 8 * tid;
@@ -1011,29 +1015,53 @@ __device__ __forceinline__ void group_barrier(int group) {
 // x~[N-1+i] = x[N-1-i]; the left padding is never read (register reflection of the first item).
 template <int F>
 __device__ __forceinline__ int root_shift(const float* xg) {
-    const int a = static_cast<int>((reinterpret_cast<uintptr_t>(xg) & 15u) >> 2);       // 0 or 2 (host-checked)
-    return (a - (F - 2)) & 3;
+    const int a = static_cast<int>((reinterpret_cast<uintptr_t>(xg) & 15u) >> 2);       // bulk staging: 0 or 2 (host-checked)
+    const int d = (a - (F - 2)) & 3;
+    return (d & 1) ? 0 : d;                                // 4-byte aligned rows (cp.async staging only): no shift, narrow copies
 }
+// The root is staged in two parts, one per half-tree group: part g is what lies in group g's half of region B (root index
+// < / >= split, a multiple of four floats, so both parts start on 16-byte boundaries in global and shared memory), and group g
+// may stage it as soon as IT has finished with that half.  Each part is one warp's work: `AFD_WPT_ROOT_COPIES` bulk copies on
+// the shared mbarrier (initialised to two arrivals, one per part) plus the scalar copies at the part's outer end.
+#ifndef AFD_WPT_ROOT_COPIES
+#define AFD_WPT_ROOT_COPIES 1
+#endif
 template <int F>
-__device__ __forceinline__ void stage_root_bulk(const float* __restrict__ xg, float* __restrict__ root, int N, uint32_t bar, int lane) {
+__device__ __forceinline__ void stage_root_bulk(const float* __restrict__ xg, float* __restrict__ root, int N, uint32_t bar, int lane,
+                                                int part, int split) {
     constexpr int padl = F - 2;
     const int a = static_cast<int>((reinterpret_cast<uintptr_t>(xg) & 15u) >> 2);
     const int d = (a - padl) & 3;
     const int s0 = (4 - a) & 3;                             // first sample at a 16-byte boundary
     const int units = (N - s0) >> 2;
     float* const dst = root + padl + d;                     // position of sample 0
-    if (lane < s0) dst[lane] = __ldg(xg + lane);
-    for (int s = s0 + 4 * units + lane; s < N; s += 32) dst[s] = __ldg(xg + s);
-    const int padr = padl + 1 + 3;                          // right padding incl. the odd-length sample and the item over-read's first floats
-    for (int j = lane; j < padr && j < N - 1; j += 32) dst[N + j] = __ldg(xg + (N - 2 - j));
-    __syncwarp();
+    int sm = split - padl - d;                              // first sample of part 1: (sm - s0) is a multiple of 4
+    sm = sm < s0 ? s0 : (sm > s0 + 4 * units ? s0 + 4 * units : sm);
+    const int b0 = part == 0 ? s0 : sm, b1 = part == 0 ? sm : s0 + 4 * units;        // this part's bulk range, in samples
     if (lane == 0) {
+        // the bulk copies first: the scalar copies below wait for their loads (a DRAM round trip) before they can store
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        const uint32_t bytes = 16u * static_cast<uint32_t>(units);
+        const uint32_t bytes = 4u * static_cast<uint32_t>(b1 - b0);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-        if (bytes)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst + s0))), "l"(xg + s0), "r"(bytes), "r"(bar) : "memory");
+        const uint32_t piece = ((bytes / AFD_WPT_ROOT_COPIES) + 15u) & ~15u;
+        uint32_t off = 0;
+#pragma unroll
+        for (int c = 0; c < AFD_WPT_ROOT_COPIES; ++c) {
+            const uint32_t nb = (c == AFD_WPT_ROOT_COPIES - 1 || off + piece > bytes) ? bytes - off : piece;
+            if (nb)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst + b0)) + off),
+                               "l"(reinterpret_cast<const char*>(xg + b0) + off), "r"(nb), "r"(bar) : "memory");
+            off += nb;
+        }
+    }
+    // by threads (visible to the CTA through the frame's first barrier, not through the mbarrier)
+    if (part == 0) {
+        if (lane < s0) dst[lane] = __ldg(xg + lane);
+    } else {
+        for (int s = s0 + 4 * units + lane; s < N; s += 32) dst[s] = __ldg(xg + s);
+        const int padr = padl + 1 + 3;                      // right padding incl. the odd-length sample and the item over-read's first floats
+        for (int j = lane; j < padr && j < N - 1; j += 32) dst[N + j] = __ldg(xg + (N - 2 - j));
     }
 }
 __device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
@@ -1053,6 +1081,11 @@ template <int F>
 struct BulkRoot {
     static constexpr bool value = F <= AFD_WPT_BULK_ROOT_MAXF;
 };
+// cp.async staging (longer filters): place the frame so that global and shared addresses agree modulo 16 bytes (16-byte copies
+// for every 8-byte aligned frame; without it coif4's root, 22 floats behind a 16-byte boundary, is staged in 8-byte pieces).
+#ifndef AFD_WPT_CPASYNC_ALIGN
+#define AFD_WPT_CPASYNC_ALIGN 1
+#endif
 
 template <int F, int R0, int RA, int RB, int RLA, int RLB, bool EXT>
 __global__ void __launch_bounds__(kFrameThreads, 1)
@@ -1079,7 +1112,7 @@ wpt_frame_kernel(const float* __restrict__ x, long long x_row_stride, long long 
     int* const s_second = reinterpret_cast<int*>(smem + plan.smem_floats + 3);
     if (tid == 0) {
         s_arrivals = 0;
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(root_bar), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(root_bar), "r"(2));       // one arrival per part of the root
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -1097,21 +1130,34 @@ wpt_frame_kernel(const float* __restrict__ x, long long x_row_stride, long long 
         const float* xg = x + b * x_row_stride;
         const long long nb = b + gridDim.x;
         constexpr bool kBulk = BulkRoot<F>::value;
+        constexpr bool kShift = kBulk || AFD_WPT_CPASYNC_ALIGN;     // sample 0 at root[F - 2 + root_shift(frame)]
         if (!prefetched) {
             if (!first) __syncthreads();                   // region B may still be read by a group's last passes
-            if constexpr (kBulk) { if (tid < 32) stage_root_bulk<F>(xg, root, plan.N, root_bar, tid); }
-            else issue_chunk<F>(xg, root, 0, plan, kFrameThreads);
+            if constexpr (kBulk) { if (gt < 32) stage_root_bulk<F>(xg, root, plan.N, root_bar, gt, group, plan.root_split); }
+            else issue_chunk<F>(xg, root + (kShift ? root_shift<F>(xg) : 0), 0, plan, kFrameThreads);
         }
         first = false;
         prefetched = false;
+#if AFD_WPT_PHASE_TIMING
+        const long long w0_ = clock64();
+#endif
         if constexpr (kBulk) {
             mbar_wait_parity(root_bar, root_parity);       // the bulk copy has landed ...
             root_parity ^= 1u;
         } else {
             cp_async_wait<0>();
         }
+#if AFD_WPT_PHASE_TIMING
+        const long long w1_ = clock64();
+#endif
         __syncthreads();                                   // ... and so have the staging warp's scalar copies
-        const bool root_sh2 = kBulk && root_shift<F>(xg) != 0;
+#if AFD_WPT_PHASE_TIMING
+        if (gt == 0) {          // per group: wait for the copy, wait for the other group
+            atomicAdd(&g_wpt_phase[16 + 4 * group], static_cast<unsigned long long>(w1_ - w0_));
+            atomicAdd(&g_wpt_phase[17 + 4 * group], static_cast<unsigned long long>(clock64() - w1_));
+        }
+#endif
+        const bool root_sh2 = kShift && root_shift<F>(xg) != 0;
         AFD_PHASE_MARK(0);
         float* out_b = out + b * C * static_cast<long long>(T) * P;
         // ---------------------------------------------------------------- passes
@@ -1120,7 +1166,7 @@ wpt_frame_kernel(const float* __restrict__ x, long long x_row_stride, long long 
             if (pi == 0) {
                 // level 1: the root's two children, all 512 threads
                 if (ps.kind == 0) {
-                    if (kBulk && root_sh2) mid_level_uniform<F, R0, true, kBulk>(smem + ps.in_off + 2, smem + ps.out_off, ps, cf, tid, kFrameThreads);
+                    if (kShift && root_sh2) mid_level_uniform<F, R0, true, kShift>(smem + ps.in_off + 2, smem + ps.out_off, ps, cf, tid, kFrameThreads);
                     else mid_level_uniform<F, R0, true, false>(smem + ps.in_off, smem + ps.out_off, ps, cf, tid, kFrameThreads);
                     __syncthreads();
                     mirror_copy<F>(smem + ps.out_off, 2, ps.n_out, ps.out_stride, tid, kFrameThreads);
@@ -1150,14 +1196,23 @@ wpt_frame_kernel(const float* __restrict__ x, long long x_row_stride, long long 
                 group_barrier(group);
             } else {
                 if (ps.prefetch) {
-                    // Region B (root + even levels) is free once BOTH groups have produced level L-1.  No CTA-wide barrier
-                    // (it would put the groups back in phase): the group that gets here second stages the next frame.
-                    if (gt == 0) s_second[group] = static_cast<int>(atomicAdd(&s_arrivals, 1u) & 1u);
-                    group_barrier(group);
-                    if (nb < B) {
-                        if constexpr (kBulk) { if (s_second[group] && gt < 32) stage_root_bulk<F>(x + nb * x_row_stride, root, plan.N, root_bar, gt); }
-                        else { if (s_second[group]) issue_chunk<F>(x + nb * x_row_stride, root, 0, plan, kGroupThreads, gt); }
-                        prefetched = true;
+                    if constexpr (kBulk) {
+                        // This group's half of region B (root + even levels) is free: it has produced level L-1 (closed by a
+                        // group barrier).  It stages its part of the next frame without waiting for the other group.
+                        if (nb < B) {
+                            if (gt < 32) stage_root_bulk<F>(x + nb * x_row_stride, root, plan.N, root_bar, gt, group, plan.root_split);
+                            prefetched = true;
+                        }
+                    } else {
+                        // Region B is free once BOTH groups have produced level L-1.  No CTA-wide barrier (it would put the
+                        // groups back in phase): the group that gets here second stages the next frame.
+                        if (gt == 0) s_second[group] = static_cast<int>(atomicAdd(&s_arrivals, 1u) & 1u);
+                        group_barrier(group);
+                        if (nb < B) {
+                            const float* xn = x + nb * x_row_stride;
+                            if (s_second[group]) issue_chunk<F>(xn, root + (kShift ? root_shift<F>(xn) : 0), 0, plan, kGroupThreads, gt);
+                            prefetched = true;
+                        }
                     }
                 }
                 if (ps.rsel == 0) last_level<F, RLA, true, EXT, true>(in, ps, T, half_base, out_b, P, cf, ep, ts, gt, kGroupThreads);
@@ -1500,6 +1555,7 @@ static int make_frame_plan(int64_t N, int F, int L, int R0, const Tuning& tu, do
     p->stride1 = L > 1 ? stride[1] : 0;
     const int root_floats = p->buf_floats + tail;
     p->region_b = 2 * half[0];
+    p->root_split = half[1];
     p->smem_floats = p->region_b + (2 * half[1] > root_floats ? 2 * half[1] : round_up(root_floats, 4));
     if (4LL * (p->smem_floats + 8) > kMaxSmemPerCta) return AFD_ERR_UNSUPPORTED;      // + the kernel's mbarrier and sync words
     auto region = [&](int l) { return (l & 1) ? 0 : p->region_b; };
@@ -1623,7 +1679,8 @@ static int launch_frame(const float* x, int64_t B, int64_t N, int64_t x_row_stri
         fprintf(stderr, "wpt frame-kernel phases F=%d B=%lld (thread-0 cycles per frame: wait, level 1, level 2, ...): ", F,
                 static_cast<long long>(B));
         for (int i = 0; i < 1 + cache.plan.npass; ++i) fprintf(stderr, "%s%.0f", i ? " " : "", h[i] / frames);
-        fprintf(stderr, " | total %.0f\n", h[31] / frames);
+        fprintf(stderr, " | total %.0f | group 0: copy wait %.0f, barrier %.0f; group 1: copy wait %.0f, barrier %.0f\n", h[31] / frames,
+                h[16] / frames, h[17] / frames, h[20] / frames, h[21] / frames);
         memset(h, 0, sizeof(h));
         cudaMemcpyToSymbol(g_wpt_phase, h, sizeof(h));
     }
