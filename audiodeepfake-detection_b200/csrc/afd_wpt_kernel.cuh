@@ -403,6 +403,9 @@ __device__ __forceinline__ void lattice2_packed(const float (&w)[WLEN], const Co
     }
 }
 
+#ifndef AFD_WPT_SH2_ALIGNED
+#define AFD_WPT_SH2_ALIGNED 1
+#endif
 template <int F, int R>
 struct Win {
     static constexpr int W = 2 * R + F - 2;   // window length
@@ -420,15 +423,30 @@ __device__ __forceinline__ void load_window(const float* __restrict__ p, float (
     }
 }
 
-// The same window from an address that is only 8-byte aligned (frame kernel: a root staged with a 2-float shift)
+// The same window from an address two floats behind a 16-byte boundary (frame kernel: a root staged with a 2-float shift).
+// 64-bit loads of lanes 2R floats apart conflict two ways (R even), so the window is loaded as NV + 1 aligned 128-bit vectors
+// from p - 2 (the two floats in front of the window and up to two behind it belong to the staged root and its tail).
 template <int NV>
 __device__ __forceinline__ void load_window_f2(const float* __restrict__ p, float (&w)[4 * NV]) {
+#if AFD_WPT_SH2_ALIGNED
+    const float4* src = reinterpret_cast<const float4*>(p - 2);
+    float4 q = src[0];
+    w[0] = q.z; w[1] = q.w;
+#pragma unroll
+    for (int v = 1; v < NV; ++v) {
+        q = src[v];
+        w[4 * v - 2] = q.x; w[4 * v - 1] = q.y; w[4 * v] = q.z; w[4 * v + 1] = q.w;
+    }
+    q = src[NV];
+    w[4 * NV - 2] = q.x; w[4 * NV - 1] = q.y;
+#else
     const float2* src = reinterpret_cast<const float2*>(p);
 #pragma unroll
     for (int v = 0; v < 2 * NV; ++v) {
         const float2 q = src[v];
         w[2 * v] = q.x; w[2 * v + 1] = q.y;
     }
+#endif
 }
 
 template <int F, int R, bool LAT, bool REFL, bool SH2 = false>
@@ -1498,7 +1516,8 @@ static int launch(const float* x, int64_t B, int64_t N, int64_t x_row_stride, fl
 // Plan of the frame kernel: full tree, level l = 2^l nodes (the nodes of half tree g are the contiguous half g), root =
 // the padded frame at the start of region B.  pass[0] is level 1 (all threads); pass[l-1], l >= 2, carries the PER-GROUP
 // parent count and group-0 offsets.  Returns AFD_ERR_UNSUPPORTED when the tree does not fit one CTA.
-static int make_frame_plan(int64_t N, int F, int L, int R0, const Tuning& tu, double level_scale, WptPlan* p) {
+static int make_frame_plan(int64_t N, int F, int L, int R0, const Tuning& tu, double level_scale, WptPlan* p,
+                           bool tune_last_stride = true) {
     int n[kMaxLevel + 1], stride[kMaxLevel + 1];
     p->N = static_cast<int>(N);
     p->L = L;
@@ -1530,6 +1549,27 @@ static int make_frame_plan(int64_t N, int F, int L, int R0, const Tuning& tu, do
         int s = round_up(n[l] + (padl > tail_l ? padl : tail_l), 4);
         if (l == L - 1) {
             if (l >= 2 && ((s >> 2) & 1) == 0) s += 4;        // lanes walk across nodes in the last level: odd 16-byte stride
+            if (l >= 2 && tune_last_stride) {
+                // ... and of the four residues that leaves modulo 32 floats, the one whose 64-bit stores (the producing pass:
+                // lanes R floats apart along a node, C items per node) need the fewest shared-memory wavefronts
+                const int parents_p = 1 << (l - 2);
+                const int rp = level_cost(parents_p, n[l], tu.RB, tu.halo) < level_cost(parents_p, n[l], tu.RA, tu.halo) ? tu.RB : tu.RA;
+                const int cp = (n[l] + rp - 1) / rp;
+                int best = s, best_w = 1 << 30;
+                for (int cand = s; cand < s + 32; cand += 8) {
+                    int waves = 0;
+                    for (int h0 = 0; h0 < parents_p * cp; h0 += 16) {         // one wavefront serves 16 lanes x 8 bytes
+                        int cnt[16] = {0}, worst = 0;
+                        for (int it = h0; it < h0 + 16 && it < parents_p * cp; ++it) {
+                            const int b = ((it / cp) * (cand / 2) + (it % cp) * (rp / 2)) & 15;
+                            worst = ++cnt[b] > worst ? cnt[b] : worst;
+                        }
+                        waves += worst;
+                    }
+                    if (waves < best_w) { best_w = waves; best = cand; }
+                }
+                s = best;
+            }
         } else if (AFD_WPT_STRIDE_CONGRUENCE && l >= 2) {
             // The consumer (level l + 1) walks its lanes along a node, 2R floats apart (conflict-free for R/2 odd), and jumps
             // to the next node after C items: with stride == C * 2R (mod 32 floats) the jump continues the same progression.
@@ -1615,7 +1655,8 @@ static int launch_frame(const float* x, int64_t B, int64_t N, int64_t x_row_stri
         memcmp(cache.taps, dec_lo, sizeof(double) * F) != 0) {
         cache.valid = false;
         Tuning tu{R0, RA, RB, RLA, RLB, true, (F / 2 - 1) * 0.5};
-        const int rc = make_frame_plan(N, F, L, R0, tu, lat.scale, &cache.plan);
+        int rc = make_frame_plan(N, F, L, R0, tu, lat.scale, &cache.plan, true);
+        if (rc == AFD_ERR_UNSUPPORTED) rc = make_frame_plan(N, F, L, R0, tu, lat.scale, &cache.plan, false);   // the tuned stride may not fit
         if (rc == AFD_ERR_UNSUPPORTED) cache_ok = -1;
         else if (rc != AFD_OK) return rc;
         else cache_ok = 1;
