@@ -365,12 +365,14 @@ haar_fast_kernel(const float* __restrict__ x, long long x_row_stride, long long 
 #endif
 #if AFD_HAAR_PHASE_TIMING
 static __device__ unsigned long long g_haar_phase[8];
-static __device__ unsigned long long g_haar_warp[16];
+static __device__ unsigned long long g_haar_warp[32];
+static __device__ unsigned long long g_haar_wphase[32][4];      // linear kernel, per warp: pass C, chunk waits, passes A/B, barrier
 #define AFD_HAAR_MARK(slot)                                                                          \
     do {                                                                                             \
-        if (lane == 0 && (warp == 0 || warp == 15)) {                                                \
+        if (lane == 0) {                                                                             \
             const long long now_ = clock64();                                                        \
-            atomicAdd(&g_haar_phase[(slot) + (warp ? 4 : 0)], static_cast<unsigned long long>(now_ - t0_)); \
+            atomicAdd(&g_haar_wphase[warp & 31][slot], static_cast<unsigned long long>(now_ - t0_)); \
+            if (warp == 0 || warp == 15) atomicAdd(&g_haar_phase[(slot) + (warp ? 4 : 0)], static_cast<unsigned long long>(now_ - t0_)); \
             t0_ = now_;                                                                              \
         }                                                                                            \
     } while (0)
@@ -668,7 +670,10 @@ __device__ __forceinline__ void haar_linear_block(uint32_t blk, int lane, int ro
 // then shifted by sh = 2 floats, which the float2 accesses of pass A and the scalar accesses of passes B / C absorb.
 // All 18 warps work; blocks and node groups are dealt by the same greedy schedule (measured costs: 1.35 : 1).
 // ================================================================================================
-constexpr int kLinChunks = 4;             // bulk copies (and mbarriers) per clip
+#ifndef AFD_HAAR_LIN_CHUNKS
+#define AFD_HAAR_LIN_CHUNKS 4
+#endif
+constexpr int kLinChunks = AFD_HAAR_LIN_CHUNKS;             // bulk copies (and mbarriers) per clip
 #ifndef AFD_HAAR_BLOCK_COST
 #define AFD_HAAR_BLOCK_COST 1.35
 #endif
@@ -744,11 +749,15 @@ haar_linear_kernel(const float* __restrict__ x, long long x_row_stride, long lon
 
     // Stage a clip (warp 0): chunk c = one bulk copy of the floats [4 f0, 4 f1) of the 16-byte aligned array that starts
     // sh floats before the clip; what does not fill a 16-byte unit at the clip's end is moved by lanes (never reads past x).
-    auto load_clip = [&](float* buf, int bufi, const float* xg) {
+    // The last unit of every clip but the batch's last one is copied whole (it runs up to 3 floats into the row padding / the
+    // next clip, x_row_stride >= N; the surplus lands where pass A's appended samples are written afterwards); only the
+    // last clip moves its <= 3 tail samples by lanes -- a load -> store pair in front of the bulk copies would hold them
+    // back by a DRAM round trip.
+    auto load_clip = [&](float* buf, int bufi, const float* xg, bool last_clip) {
         const int sh = shift_of(xg);
         const float* src = xg - sh;                                        // 16-byte aligned
-        const int total4 = (N + sh) >> 2;                                  // whole float4 units inside the clip
-        for (int s = 4 * total4 - sh + lane; s < N; s += 32) buf[sh + s] = __ldg(xg + s);     // <= 3 tail samples
+        const int whole4 = (N + sh) >> 2;                                  // whole float4 units inside the clip
+        const int total4 = last_clip ? whole4 : (N + sh + 3) >> 2;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic accesses of the free buffer before the async writes
         __syncwarp();
         if (lane < kLinChunks) {
@@ -768,6 +777,8 @@ haar_linear_kernel(const float* __restrict__ x, long long x_row_stride, long lon
                              ::"r"(dst), "l"(src + 4 * f0), "r"(bytes), "r"(bar) : "memory");
             }
         }
+        if (last_clip)
+            for (int s = 4 * whole4 - sh + lane; s < N; s += 32) buf[sh + s] = __ldg(xg + s);     // <= 3 tail samples
     };
     auto wait_chunk = [&](int bufi, int c, uint32_t parity) {
         const uint32_t a = mbar(bufi, c);
@@ -811,7 +822,10 @@ haar_linear_kernel(const float* __restrict__ x, long long x_row_stride, long lon
     long long it = 0;
     if (blockIdx.x < B) {
         const float* xg = x + blockIdx.x * x_row_stride;
-        if (warp == 0) load_clip(buf0, 0, xg);
+        if (warp == 0) {
+            load_clip(buf0, 0, xg, blockIdx.x == B - 1);
+        }
+        if (blockIdx.x == B - 1) __syncthreads();      // CTA-uniform: the last clip's tail samples are stored by warp 0's lanes
         const int sh = shift_of(xg);
 #pragma unroll
         for (int t = 0; t < kMaxBlocksPerWarp; ++t)
@@ -829,7 +843,7 @@ haar_linear_kernel(const float* __restrict__ x, long long x_row_stride, long lon
 #if AFD_HAAR_PHASE_TIMING
         const long long it0_ = clock64();
 #endif
-        if (more && warp == 0) load_clip(nbuf, cur ^ 1, xn);              // the other buffer's pass C ended before the last barrier
+        if (more && warp == 0) load_clip(nbuf, cur ^ 1, xn, clip + gridDim.x == B - 1);   // the other buffer's pass C ended before the last barrier
         // ---- pass C of this clip: levels 11-L, lane = level-10 node of one of the warp's groups; |c| accumulates in registers
         const float* lin = buf + shift_of(x + clip * x_row_stride);
 #pragma unroll
@@ -1070,13 +1084,22 @@ extern "C" int afd_haar_fingerprint_accum(const float* x, int64_t B, int64_t N, 
                 cudaDeviceSynchronize();
                 cudaMemcpyFromSymbol(h, g_haar_phase, sizeof(h));
                 const double clips = static_cast<double>(B);
-                unsigned long long hw[16];
+                unsigned long long hw[32];
                 cudaMemcpyFromSymbol(hw, g_haar_warp, sizeof(hw));
                 fprintf(stderr, "haar linear: cycles from iteration start to barrier arrival per warp:");
                 for (int w = 0; w < 16; ++w) fprintf(stderr, " %.0f", hw[w] / static_cast<double>(B));
                 fprintf(stderr, "\n");
                 memset(hw, 0, sizeof(hw));
                 cudaMemcpyToSymbol(g_haar_warp, hw, sizeof(hw));
+                {
+                    static unsigned long long wp[32][4];
+                    cudaMemcpyFromSymbol(wp, g_haar_wphase, sizeof(wp));
+                    for (int w = 0; w < 20; ++w)
+                        fprintf(stderr, "  warp %2d: C %5.0f  wait %5.0f  AB %5.0f  barrier %5.0f\n", w, wp[w][0] / clips, wp[w][1] / clips,
+                                wp[w][2] / clips, wp[w][3] / clips);
+                    memset(wp, 0, sizeof(wp));
+                    cudaMemcpyToSymbol(g_haar_wphase, wp, sizeof(wp));
+                }
                 fprintf(stderr, "haar linear phases (cycles per clip; C, wait, AB, barrier) warp0: %.0f %.0f %.0f %.0f | warp15: %.0f %.0f %.0f %.0f\n",
                         h[0] / clips, h[1] / clips, h[2] / clips, h[3] / clips, h[4] / clips, h[5] / clips, h[6] / clips, h[7] / clips);
                 memset(h, 0, sizeof(h));
