@@ -674,6 +674,9 @@ __device__ __forceinline__ void haar_linear_block(uint32_t blk, int lane, int ro
 #define AFD_HAAR_LIN_CHUNKS 4
 #endif
 constexpr int kLinChunks = AFD_HAAR_LIN_CHUNKS;             // bulk copies (and mbarriers) per clip
+#ifndef AFD_HAAR_EARLY_PAIRS
+#define AFD_HAAR_EARLY_PAIRS 1
+#endif
 #ifndef AFD_HAAR_BLOCK_COST
 #define AFD_HAAR_BLOCK_COST 1.35
 #endif
@@ -905,7 +908,7 @@ haar_linear_kernel(const float* __restrict__ x, long long x_row_stride, long lon
 }
 
 static bool make_stream_schedule(int n10, int workers, int max_groups, signed char (*blocks)[kMaxBlocksPerWarp], signed char (*groups)[kMaxGroupsPerWarp],
-                                 double block_cost) {
+                                 double block_cost, bool early_pairs = false) {
     if (n10 > workers * kMaxBlocksPerWarp || 32 > workers * max_groups) return false;
     double load[kLinMaxWarps] = {0};
     int nb[kLinMaxWarps] = {0}, ng[kLinMaxWarps] = {0};
@@ -920,11 +923,28 @@ static bool make_stream_schedule(int n10, int workers, int max_groups, signed ch
             if (cnt[w] < cap && (best < 0 || load[w] < load[best])) best = w;
         return best;
     };
-    for (int b = 0; b < n10; ++b) {
-        const int w = least(nb, kMaxBlocksPerWarp);
-        if (w < 0) return false;
-        blocks[w][nb[w]++] = static_cast<signed char>(b);
-        load[w] += block_cost;
+    const int pairs = early_pairs && n10 > workers && n10 <= 2 * workers && kMaxBlocksPerWarp >= 2 ? n10 - workers : 0;
+    if (pairs > 0) {
+        // Linear kernel: the warps that own two blocks are the critical path of a clip (pass C, then both blocks, each as soon as
+        // its chunk has landed), so they take the blocks that land FIRST (w and pairs + w: chunks 0 / 1); the one-block warps run two
+        // node groups of pass C before they need their block and take the later ones, the last (appended rows) among them.
+        for (int w = 0; w < workers; ++w) {
+            if (w < pairs) {
+                blocks[w][nb[w]++] = static_cast<signed char>(w);
+                blocks[w][nb[w]++] = static_cast<signed char>(pairs + w);
+                load[w] += 2 * block_cost;
+            } else {
+                blocks[w][nb[w]++] = static_cast<signed char>(pairs + w);
+                load[w] += block_cost;
+            }
+        }
+    } else {
+        for (int b = 0; b < n10; ++b) {
+            const int w = least(nb, kMaxBlocksPerWarp);
+            if (w < 0) return false;
+            blocks[w][nb[w]++] = static_cast<signed char>(b);
+            load[w] += block_cost;
+        }
     }
     for (int g = 0; g < 32; ++g) {
         const int w = least(ng, max_groups);
@@ -948,7 +968,7 @@ static bool make_linear_plan(const HaarFastPlan& fp, HaarLinearPlan* lp) {
     for (int c = 0; c <= kLinChunks; ++c) lp->chunk_first[c] = static_cast<int>(static_cast<long long>(fp.n10) * c / kLinChunks);
     // measured (phase table): a block's passes A + B take ~1.75 k cycles, a node group's pass C ~1.3 k
     return make_stream_schedule(fp.n10, kLinWarps, kLinGroups < kMaxGroupsPerWarp ? kLinGroups : kMaxGroupsPerWarp, lp->blocks, lp->groups,
-                                AFD_HAAR_BLOCK_COST);
+                                AFD_HAAR_BLOCK_COST, AFD_HAAR_EARLY_PAIRS != 0);
 }
 
 // Greedy schedule: blocks (cost 2.4) then node groups (cost 1) to the least loaded warp.
