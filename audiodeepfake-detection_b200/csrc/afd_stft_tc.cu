@@ -480,7 +480,7 @@ stft_tc511_kernel(const float* __restrict__ x, long long x_row_stride, float* __
             // the other tile is rewritten only after every thread passed the next unit's barrier
         }
         if (!EXT && warp == 0 && lane < kRows) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        PROF_PRINT(tid == 0 || tid == 133, "epi: wait d_full / combine / bar / store");
+        PROF_PRINT((tid & 31) == 5, "epi: wait d_full / combine / bar / store");   // one thread of every epilogue warp
         if (EXT && p.moments) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
