@@ -1676,7 +1676,11 @@ static int launch_frame(const float* x, int64_t B, int64_t N, int64_t x_row_stri
         }
         if (cache_ok > 0) {
             const char* stg = getenv("AFD_WPT_STAGGER");  // tuning knob (cycles); default measured on B200
-            cache.plan.stagger = stg ? atoi(stg) : (F <= 16 ? AFD_WPT_STAGGER_DEFAULT : AFD_WPT_STAGGER_DEFAULT / 3);   // sweep: sym5 best at 1200, coif4 at 400
+            // sweeps (tools/gpu_stagger_sweep.sh, B = 4096, level 8): db2 / db3 best at 1000, sym4 / sym5 / coif2 at 1200, db7 / sym8 at
+            // 1600 cycles; the filters staged with cp.async (F > 16) at 0 - 400
+            cache.plan.stagger = stg ? atoi(stg)
+                                     : (F <= 6 ? AFD_WPT_STAGGER_DEFAULT * 5 / 6
+                                               : F <= 12 ? AFD_WPT_STAGGER_DEFAULT : F <= 16 ? AFD_WPT_STAGGER_DEFAULT * 4 / 3 : AFD_WPT_STAGGER_DEFAULT / 3);
             Coefs<F>& cf = cache.cf;
             for (int k = 0; k < F; ++k) {
                 cf.lo[k] = static_cast<float>(dec_lo[k]);
