@@ -157,3 +157,22 @@ def test_plan_info_headline_shapes_fit_one_frame_cta():
         assert npass.value == 8                                     # levels 1..8
         assert 256 < items[0] <= 512                                # level 1: one round of the whole CTA
         assert all(0 < items[i] <= 256 for i in range(1, npass.value))  # one round of a group's 256 threads per level
+
+def test_plan_info_every_tabulated_wavelet_plans_within_shared_memory():
+    """Every filter that ships a table gets a plan for the BASELINE frame length at level 8 that fits one SM's shared memory
+    (the frame kernel's tuned last stride falls back to the untuned one when it would not fit)."""
+    from audiodeepfake_detection_b200 import _wavelet_tables
+    from audiodeepfake_detection_b200.wavelets import Wavelet
+
+    lib = _lib.load()
+    names = sorted(getattr(_wavelet_tables, "DEC_LO", getattr(_wavelet_tables, "TABLES", {})).keys())
+    assert len(names) >= 40
+    for name in names:
+        taps = Wavelet(name).dec_lo
+        c_taps = (ctypes.c_double * len(taps))(*taps)
+        smem, ctas, lat, npass = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        items, rs = (ctypes.c_int * 24)(), (ctypes.c_int * 24)()
+        rc = lib.afd_wpt_plan_info(22050, c_taps, len(taps), 8, ctypes.byref(smem), ctypes.byref(ctas),
+                                   ctypes.byref(lat), ctypes.byref(npass), items, rs)
+        assert rc == 0, (name, rc)
+        assert 0 < smem.value <= 232448 and ctas.value in (1, 2) and npass.value >= 7, (name, smem.value, ctas.value, npass.value)   # two-CTA kernel: level 1 is not a pass
